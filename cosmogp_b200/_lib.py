@@ -1,0 +1,104 @@
+"""ctypes binding of libcosmogp_b200.so (include/cosmogp_b200.h).
+
+The library is the ONLY compute path of this package: there is no CPU fallback.
+Loading fails loudly when the shared object is missing, and every compute call
+fails loudly when no CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcosmogp_b200.so")
+
+CGP_AMP_ON_AUTOCOV = 1
+CGP_SMALL_MAX_N = 224
+CGP_LOO_PLAIN = 0
+CGP_LOO_RECENTER = 1
+
+_i64 = C.c_int64
+_int = C.c_int
+_dbl = C.c_double
+_ptr = C.c_void_p
+_u32 = C.c_uint
+
+# name -> (restype, argtypes); mirrors include/cosmogp_b200.h one to one
+_BATCH = [_i64, _ptr, _int]                      # n_obj, off, dim   (host flavour)
+_BATCH_DEV = [_i64, _ptr, _int, _int]            # n_obj, off, max_n, dim
+_HYP = [_ptr, _dbl, _dbl, _u32]                  # hyp, nugget, floor, flags
+SIGNATURES = {
+    "cgp_version": (_int, []),
+    "cgp_last_error": (C.c_char_p, []),
+    "cgp_device_count": (_int, []),
+    "cgp_fp64_peak": (_int, [_int, C.POINTER(_dbl)]),
+    "cgp_launch_count": (_i64, []),
+    "cgp_ll_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_ptr, _ptr, _ptr]),
+    "cgp_ll_batched_host": (_int, _BATCH + [_ptr] * 4 + _HYP + [_ptr, _ptr, C.POINTER(_dbl)]),
+    "cgp_predict_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "cgp_predict_batched_host": (_int, _BATCH + [_ptr] * 4 + _HYP + [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "cgp_loo_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_int] + [_ptr] * 4 + [_ptr, _ptr]),
+    "cgp_loo_batched_host": (_int, _BATCH + [_ptr] * 4 + _HYP + [_int] + [_ptr] * 4 + [_ptr]),
+    "cgp_matrices_batched_dev": (_int, _BATCH_DEV + [_ptr] * 2 + _HYP + [_ptr, _ptr, _ptr, _ptr, _ptr]),
+}
+
+_lib = None
+
+
+class CosmogpB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  No fallback: a missing or unloadable
+    library is an error the caller sees."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CosmogpB200Error(
+                "%s not found: build it with `python -m cosmogp_b200.build` (nvcc, sm_100a). "
+                "cosmogp_b200 has no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the header and the .so disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().cgp_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    """rc < 0 -> raise; rc >= 0 -> number of non-positive-definite objects."""
+    if rc < 0:
+        raise CosmogpB200Error("%s failed (%d): %s" % (what, rc, last_error()))
+    return rc
+
+
+def require_device():
+    n = lib().cgp_device_count()
+    if n <= 0:
+        raise CosmogpB200Error("no CUDA device visible (%s); cosmogp_b200 has no CPU fallback"
+                               % (last_error() if n < 0 else "device count 0"))
+    return n
+
+
+def hptr(a):
+    """Host pointer of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def fp64_peak(kind=1):
+    out = _dbl(0.0)
+    check(lib().cgp_fp64_peak(kind, C.byref(out)), "cgp_fp64_peak")
+    return out.value

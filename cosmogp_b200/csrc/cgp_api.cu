@@ -1,0 +1,319 @@
+// C ABI of cosmogp_b200 (see include/cosmogp_b200.h for the contract and the
+// reference interfaces each entry point replaces).  No C++ exception crosses it.
+#include "../../include/cosmogp_b200.h"
+#include "cgp_internal.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace cgp {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void count_launch(int n) { g_launches += n; }
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(int e, const char* where) {
+  return fail(-100 - e, "%s: CUDA error %d (%s)", where, e, cudaGetErrorString((cudaError_t)e));
+}
+
+#define CGP_ERR_ARG   (-1)
+#define CGP_ERR_SIZE  (-2)
+
+// hyp -> Cov  (cosmogp/kernel.py:71-75 for 1D, :127-151 for 2D)
+static int make_cov(int dim, const double* hyp, double nugget, double floor, unsigned flags, Cov* c) {
+  if (!hyp) return fail(CGP_ERR_ARG, "hyp is NULL");
+  const double s2 = hyp[0] * hyp[0];
+  if (dim == 1) {
+    c->amp_auto = s2; c->amp_cross = s2;
+    c->m00 = 1.0 / (hyp[1] * hyp[1]); c->m01x2 = 0.0; c->m11 = 0.0;
+  } else if (dim == 2) {
+    const double lx2 = hyp[1] * hyp[1], ly2 = hyp[2] * hyp[2], lxy = hyp[3];
+    const double sc = 1.0 / (lx2 * ly2 - lxy * lxy);        // NaN/inf metric propagates, like scipy
+    c->m00 = ly2 * sc; c->m01x2 = 2.0 * (-lxy * sc); c->m11 = lx2 * sc;
+    c->amp_cross = s2;
+    c->amp_auto = (flags & CGP_AMP_ON_AUTOCOV) ? s2 : 1.0;  // HEAD drops sigma^2 (kernel.py:146-148)
+  } else {
+    return fail(CGP_ERR_ARG, "dim must be 1 or 2, got %d", dim);
+  }
+  c->noise_const = floor * floor + nugget * nugget;
+  c->nugget2 = nugget * nugget;
+  return 0;
+}
+
+static int max_n_from_device(int64_t n_obj, const int64_t* off_dev, cudaStream_t st, int* max_n) {
+  std::vector<int64_t> h((size_t)n_obj + 1);
+  cudaError_t e = cudaMemcpyAsync(h.data(), off_dev, sizeof(int64_t) * (n_obj + 1), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail((int)e, "read off[]");
+  int64_t m = 0;
+  for (int64_t i = 0; i < n_obj; ++i) { int64_t n = h[i + 1] - h[i]; if (n > m) m = n; }
+  *max_n = (int)m;
+  return 0;
+}
+static int max_n_host(int64_t n_obj, const int64_t* off) {
+  int64_t m = 0;
+  for (int64_t i = 0; i < n_obj; ++i) { int64_t n = off[i + 1] - off[i]; if (n > m) m = n; }
+  return (int)m;
+}
+
+static int run_small(Task task, int dim, int max_n, SmallArgs& a, cudaStream_t st, const char* who) {
+  if (a.n_obj == 0) return 0;
+  if (max_n > CGP_SMALL_MAX_N)
+    return fail(CGP_ERR_SIZE, "%s: object with %d points exceeds the shared-memory path (max %d); "
+                "use the large-object entry points", who, max_n, CGP_SMALL_MAX_N);
+  int e = launch_small(task, dim, max_n, a, st);
+  if (e) return cuda_fail(e, who);
+  return 0;
+}
+
+// ---- tiny RAII helpers for the _host entry points ------------------------------------
+struct DevBuf {
+  void* p = nullptr; cudaStream_t st;
+  explicit DevBuf(cudaStream_t s) : st(s) {}
+  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 8, st); }
+  template <class T> T* as() { return (T*)p; }
+};
+struct HostCall {
+  cudaStream_t st = nullptr; cudaError_t err = cudaSuccess;
+  HostCall() { err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); }
+  ~HostCall() { if (st) cudaStreamDestroy(st); }
+  // upload n elements (or leave null when the host pointer is null)
+  template <class T> const T* up(DevBuf& b, const T* h, size_t n) {
+    if (!h || err != cudaSuccess) return nullptr;
+    err = b.alloc(n * sizeof(T));
+    if (err == cudaSuccess) err = cudaMemcpyAsync(b.p, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return b.as<T>();
+  }
+  template <class T> T* out(DevBuf& b, const T* h, size_t n) {
+    if (!h || err != cudaSuccess) return nullptr;
+    err = b.alloc(n * sizeof(T));
+    return b.as<T>();
+  }
+  template <class T> void down(T* h, DevBuf& b, size_t n) {
+    if (!h || err != cudaSuccess) return;
+    err = cudaMemcpyAsync(h, b.p, n * sizeof(T), cudaMemcpyDeviceToHost, st);
+  }
+  bool sync() { if (err == cudaSuccess) err = cudaStreamSynchronize(st); return err == cudaSuccess; }
+};
+
+static int count_bad(const int* info, int64_t n) {
+  int64_t c = 0;
+  for (int64_t i = 0; i < n; ++i) c += info[i] != 0;
+  return c > 2147483647 ? 2147483647 : (int)c;
+}
+
+}  // namespace cgp
+
+using namespace cgp;
+
+extern "C" {
+
+int cgp_version(void) { return 100; }
+const char* cgp_last_error(void) { return g_err; }
+int64_t cgp_launch_count(void) { return g_launches.load(); }
+
+int cgp_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail((int)e, "cgp_device_count");
+  return n;
+}
+
+int cgp_fp64_peak(int kind, double* tflops) {
+  if (!tflops || kind < 0 || kind > 1) return fail(CGP_ERR_ARG, "cgp_fp64_peak: bad arguments");
+  int e = measure_fp64_peak(kind, tflops);
+  return e ? cuda_fail(e, "cgp_fp64_peak") : 0;
+}
+
+// ------------------------------------------------------------------------------------ LL
+int cgp_ll_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                       const double* x, const double* y, const double* y0, const double* y_err,
+                       const double* hyp, double nugget, double floor, unsigned flags,
+                       double* ll_obj, int* info, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !ll_obj || !info)))
+    return fail(CGP_ERR_ARG, "cgp_ll_batched_dev: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  SmallArgs a; memset(&a, 0, sizeof a);
+  int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
+  if (rc) return rc;
+  if (n_obj && max_n <= 0 && (rc = max_n_from_device(n_obj, off, st, &max_n))) return rc;
+  a.n_obj = n_obj; a.off = off; a.x = x; a.y = y; a.y0 = y0; a.yerr = y_err;
+  a.ll = ll_obj; a.info = info;
+  return run_small(TASK_LL, dim, max_n, a, st, "cgp_ll_batched_dev");
+}
+
+int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
+                        const double* x, const double* y, const double* y0, const double* y_err,
+                        const double* hyp, double nugget, double floor, unsigned flags,
+                        double* ll_obj, int* info, double* ll_sum) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !ll_obj || !info)))
+    return fail(CGP_ERR_ARG, "cgp_ll_batched_host: NULL argument");
+  if (ll_sum) *ll_sum = 0.0;
+  if (n_obj == 0) return 0;
+  const size_t np = (size_t)off[n_obj];
+  HostCall hc;
+  DevBuf b_off(hc.st), b_x(hc.st), b_y(hc.st), b_y0(hc.st), b_e(hc.st), b_ll(hc.st), b_info(hc.st);
+  const int64_t* d_off = hc.up(b_off, off, (size_t)n_obj + 1);
+  const double* d_x = hc.up(b_x, x, np * dim);
+  const double* d_y = hc.up(b_y, y, np);
+  const double* d_y0 = hc.up(b_y0, y0, np);
+  const double* d_e = hc.up(b_e, y_err, np);
+  double* d_ll = hc.out(b_ll, ll_obj, (size_t)n_obj);
+  int* d_info = hc.out(b_info, info, (size_t)n_obj);
+  if (hc.err != cudaSuccess) return cuda_fail((int)hc.err, "cgp_ll_batched_host (upload)");
+  int rc = cgp_ll_batched_dev(n_obj, d_off, max_n_host(n_obj, off), dim, d_x, d_y, d_y0, d_e, hyp, nugget, floor,
+                              flags, d_ll, d_info, hc.st);
+  if (rc) return rc;
+  hc.down(ll_obj, b_ll, (size_t)n_obj);
+  hc.down(info, b_info, (size_t)n_obj);
+  if (!hc.sync()) return cuda_fail((int)hc.err, "cgp_ll_batched_host");
+  if (ll_sum) { double s = 0.0; for (int64_t i = 0; i < n_obj; ++i) s += ll_obj[i]; *ll_sum = s; }
+  return count_bad(info, n_obj);
+}
+
+// ------------------------------------------------------------------------------------ predict
+int cgp_predict_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                            const double* x, const double* y, const double* y0, const double* y_err,
+                            const double* hyp, double nugget, double floor, unsigned flags,
+                            const double* xnew, const int64_t* goff, int64_t m_shared,
+                            const double* new_y0, double* mean, double* var, int* info, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !xnew || !mean || !info)))
+    return fail(CGP_ERR_ARG, "cgp_predict_batched_dev: NULL argument");
+  if (!goff && m_shared < 0) return fail(CGP_ERR_ARG, "cgp_predict_batched_dev: m_shared < 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  SmallArgs a; memset(&a, 0, sizeof a);
+  int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
+  if (rc) return rc;
+  if (n_obj && max_n <= 0 && (rc = max_n_from_device(n_obj, off, st, &max_n))) return rc;
+  a.n_obj = n_obj; a.off = off; a.x = x; a.y = y; a.y0 = y0; a.yerr = y_err; a.info = info;
+  a.xnew = xnew; a.goff = goff; a.m_shared = m_shared; a.new_y0 = new_y0; a.mean = mean; a.var = var;
+  // few objects with long grids: several CTAs per object, each refactorising (cheap) and
+  // taking every split-th block of 8 grid points
+  int split = 1;
+  if (!goff && n_obj < 296) {
+    const int64_t rbs = (m_shared + 7) / 8;
+    int64_t want = 592 / (n_obj > 0 ? n_obj : 1);
+    int64_t cap = (rbs + 3) / 4;
+    if (want > cap) want = cap;
+    if (want > 1) split = (int)want;
+  }
+  a.split = split;
+  return run_small(TASK_PREDICT, dim, max_n, a, st, "cgp_predict_batched_dev");
+}
+
+int cgp_predict_batched_host(int64_t n_obj, const int64_t* off, int dim,
+                             const double* x, const double* y, const double* y0, const double* y_err,
+                             const double* hyp, double nugget, double floor, unsigned flags,
+                             const double* xnew, const int64_t* goff, int64_t m_shared,
+                             const double* new_y0, double* mean, double* var, int* info) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !xnew || !mean || !info)))
+    return fail(CGP_ERR_ARG, "cgp_predict_batched_host: NULL argument");
+  if (n_obj == 0) return 0;
+  const size_t np = (size_t)off[n_obj];
+  const size_t ng = goff ? (size_t)goff[n_obj] : (size_t)m_shared;        // grid points stored
+  const size_t nout = goff ? (size_t)goff[n_obj] : (size_t)n_obj * (size_t)m_shared;
+  HostCall hc;
+  DevBuf b_off(hc.st), b_x(hc.st), b_y(hc.st), b_y0(hc.st), b_e(hc.st), b_g(hc.st), b_goff(hc.st),
+      b_ny0(hc.st), b_mean(hc.st), b_var(hc.st), b_info(hc.st);
+  const int64_t* d_off = hc.up(b_off, off, (size_t)n_obj + 1);
+  const double* d_x = hc.up(b_x, x, np * dim);
+  const double* d_y = hc.up(b_y, y, np);
+  const double* d_y0 = hc.up(b_y0, y0, np);
+  const double* d_e = hc.up(b_e, y_err, np);
+  const double* d_g = hc.up(b_g, xnew, ng * dim);
+  const int64_t* d_goff = hc.up(b_goff, goff, (size_t)n_obj + 1);
+  const double* d_ny0 = hc.up(b_ny0, new_y0, nout);
+  double* d_mean = hc.out(b_mean, mean, nout);
+  double* d_var = hc.out(b_var, var, nout);
+  int* d_info = hc.out(b_info, info, (size_t)n_obj);
+  if (hc.err != cudaSuccess) return cuda_fail((int)hc.err, "cgp_predict_batched_host (upload)");
+  int rc = cgp_predict_batched_dev(n_obj, d_off, max_n_host(n_obj, off), dim, d_x, d_y, d_y0, d_e, hyp, nugget,
+                                   floor, flags, d_g, d_goff, m_shared, d_ny0, d_mean, d_var, d_info, hc.st);
+  if (rc) return rc;
+  hc.down(mean, b_mean, nout);
+  hc.down(var, b_var, nout);
+  hc.down(info, b_info, (size_t)n_obj);
+  if (!hc.sync()) return cuda_fail((int)hc.err, "cgp_predict_batched_host");
+  return count_bad(info, n_obj);
+}
+
+// ------------------------------------------------------------------------------------ LOO
+int cgp_loo_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                        const double* x, const double* y, const double* m, const double* y_err,
+                        const double* hyp, double nugget, double floor, unsigned flags, int mode,
+                        double* pred, double* pred_var, double* pull, double* resid,
+                        int* info, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !info)))
+    return fail(CGP_ERR_ARG, "cgp_loo_batched_dev: NULL argument");
+  if (mode != CGP_LOO_PLAIN && mode != CGP_LOO_RECENTER) return fail(CGP_ERR_ARG, "cgp_loo_batched_dev: bad mode %d", mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  SmallArgs a; memset(&a, 0, sizeof a);
+  int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
+  if (rc) return rc;
+  if (n_obj && max_n <= 0 && (rc = max_n_from_device(n_obj, off, st, &max_n))) return rc;
+  a.n_obj = n_obj; a.off = off; a.x = x; a.y = y; a.y0 = m; a.yerr = y_err; a.info = info;
+  a.loo_mode = mode; a.pred = pred; a.pvar = pred_var; a.pull = pull; a.resid = resid;
+  return run_small(TASK_LOO, dim, max_n, a, st, "cgp_loo_batched_dev");
+}
+
+int cgp_loo_batched_host(int64_t n_obj, const int64_t* off, int dim,
+                         const double* x, const double* y, const double* m, const double* y_err,
+                         const double* hyp, double nugget, double floor, unsigned flags, int mode,
+                         double* pred, double* pred_var, double* pull, double* resid, int* info) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !info)))
+    return fail(CGP_ERR_ARG, "cgp_loo_batched_host: NULL argument");
+  if (n_obj == 0) return 0;
+  const size_t np = (size_t)off[n_obj];
+  HostCall hc;
+  DevBuf b_off(hc.st), b_x(hc.st), b_y(hc.st), b_m(hc.st), b_e(hc.st), b_p(hc.st), b_v(hc.st), b_pl(hc.st),
+      b_r(hc.st), b_info(hc.st);
+  const int64_t* d_off = hc.up(b_off, off, (size_t)n_obj + 1);
+  const double* d_x = hc.up(b_x, x, np * dim);
+  const double* d_y = hc.up(b_y, y, np);
+  const double* d_m = hc.up(b_m, m, np);
+  const double* d_e = hc.up(b_e, y_err, np);
+  double* d_p = hc.out(b_p, pred, np);
+  double* d_v = hc.out(b_v, pred_var, np);
+  double* d_pl = hc.out(b_pl, pull, np);
+  double* d_r = hc.out(b_r, resid, np);
+  int* d_info = hc.out(b_info, info, (size_t)n_obj);
+  if (hc.err != cudaSuccess) return cuda_fail((int)hc.err, "cgp_loo_batched_host (upload)");
+  int rc = cgp_loo_batched_dev(n_obj, d_off, max_n_host(n_obj, off), dim, d_x, d_y, d_m, d_e, hyp, nugget, floor,
+                               flags, mode, d_p, d_v, d_pl, d_r, d_info, hc.st);
+  if (rc) return rc;
+  hc.down(pred, b_p, np); hc.down(pred_var, b_v, np); hc.down(pull, b_pl, np); hc.down(resid, b_r, np);
+  hc.down(info, b_info, (size_t)n_obj);
+  if (!hc.sync()) return cuda_fail((int)hc.err, "cgp_loo_batched_host");
+  return count_bad(info, n_obj);
+}
+
+// ------------------------------------------------------------------------------------ matrices
+int cgp_matrices_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                             const double* x, const double* y_err,
+                             const double* hyp, double nugget, double floor, unsigned flags,
+                             const int64_t* moff, double* kmat, double* kinv, int* info, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !moff || !info)))
+    return fail(CGP_ERR_ARG, "cgp_matrices_batched_dev: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  SmallArgs a; memset(&a, 0, sizeof a);
+  int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
+  if (rc) return rc;
+  if (n_obj && max_n <= 0 && (rc = max_n_from_device(n_obj, off, st, &max_n))) return rc;
+  a.n_obj = n_obj; a.off = off; a.x = x; a.yerr = y_err; a.info = info;
+  a.moff = moff; a.kmat = kmat; a.kinv = kinv;
+  return run_small(TASK_MATRICES, dim, max_n, a, st, "cgp_matrices_batched_dev");
+}
+
+}  // extern "C"

@@ -1,0 +1,565 @@
+// Small-object Gaussian-process kernels for B200 (sm_100a): objects of N <= 224 points,
+// one warp (N <= 64) or one 4-warp CTA per object, everything resident in shared memory.
+//
+// What one object costs the reference (citations into PFLeget/cosmogp):
+//   K = kernel(x, hyp, nugget, y_err)          cosmogp/kernel.py:25-77 / 80-155
+//   inv, logdet = cholesky_inverse(K)          cosmogp/inv_matrix.py:21-31
+//   LL (Gaussian_process.py:68-73), mean / covariance (:332-335, :356-361),
+//   leave-one-out pulls (pull.py:66-94)
+// Here K is never written to HBM.  It is generated tile by tile (8x8) straight into
+// DMMA accumulator registers, factorised by a left-looking block Cholesky whose
+// rank-8 updates, triangular solves, L^-1 and L^-1-applications all run on the FP64
+// tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), and consumed in place.
+//
+// Tile storage ("fragment order"): element (r, c) of an 8x8 tile lives at
+//   (r*4 + (c&3))*2 + (c>>2)
+// so that lane (g = lane/4, t = lane%4) fetches both k-halves of its DMMA A/B fragment
+// {tile[g][t], tile[g][4+t]} with ONE conflict-free 16-byte load at lane*2, and the
+// transposed fragment {tile[t][g], tile[4+t][g]} with two conflict-free 8-byte loads.
+// With the m8n8k4 layouts (A[g][t], B[t][g], C[g][2t..2t+1]) this gives, with no
+// data movement, all three products the algorithm needs:
+//   X*Y^T (frag, frag)   X*Y (frag, fragT)   X^T*Y (fragT, fragT).
+#include "cgp_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+
+namespace cgp {
+namespace {
+
+constexpr int TILE = 64;                      // doubles per 8x8 tile
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ int slot(int i, int j) { return ((i * (i + 1)) >> 1) + j; }   // i >= j
+__host__ __device__ __forceinline__ int frag_off(int r, int c) { return ((r * 4 + (c & 3)) << 1) + (c >> 2); }
+
+struct Lane {
+  int g, t;
+  int fr;          // lane*2: this lane's fragment pair
+  int st0, st1;    // where accumulator elements (g,2t), (g,2t+1) go
+  int tr0, tr1;    // transposed fragment: (t,g), (4+t,g)
+  __device__ explicit Lane(int lane) {
+    g = lane >> 2; t = lane & 3; fr = lane << 1;
+    st0 = frag_off(g, 2 * t); st1 = frag_off(g, 2 * t + 1);
+    tr0 = frag_off(t, g); tr1 = frag_off(4 + t, g);
+  }
+};
+
+__device__ __forceinline__ double2 ld_frag(const double* tiles, int s, const Lane& L) {
+  return *reinterpret_cast<const double2*>(tiles + s * TILE + L.fr);
+}
+__device__ __forceinline__ double2 ld_fragT(const double* tiles, int s, const Lane& L) {
+  const double* p = tiles + s * TILE;
+  return make_double2(p[L.tr0], p[L.tr1]);
+}
+__device__ __forceinline__ void st_acc(double* tiles, int s, const Lane& L, double c0, double c1) {
+  double* p = tiles + s * TILE;
+  p[L.st0] = c0; p[L.st1] = c1;
+}
+__device__ __forceinline__ double red_t(double v) {     // sum over the 4 lanes of a row group
+  v += __shfl_xor_sync(FULL, v, 1); v += __shfl_xor_sync(FULL, v, 2); return v;
+}
+__device__ __forceinline__ double red_g(double v) {     // sum over the 8 row groups
+  v += __shfl_xor_sync(FULL, v, 4); v += __shfl_xor_sync(FULL, v, 8); v += __shfl_xor_sync(FULL, v, 16);
+  return v;
+}
+__device__ __forceinline__ double red_warp(double v) { return red_g(red_t(v)); }
+
+template <int WARPS> __device__ __forceinline__ void cta_sync() {
+  if (WARPS == 1) __syncwarp(); else __syncthreads();
+}
+
+// q/2 exponent of the RBF: 1D (a-b)^2/l^2, 2D Mahalanobis form under the inverse metric.
+template <int DIM>
+__device__ __forceinline__ double rbf(const Cov& c, double amp, double ax, double ay, double bx, double by) {
+  double dx = ax - bx;
+  double q;
+  if (DIM == 1) {
+    q = dx * dx * c.m00;
+  } else {
+    double dy = ay - by;
+    q = dx * dx * c.m00 + dx * dy * c.m01x2 + dy * dy * c.m11;
+  }
+  return amp * exp(-0.5 * q);
+}
+
+// In-register Cholesky of one 8x8 diagonal tile held in accumulator layout (lower
+// triangle valid), returning T = L^-1 in the same layout, the product of the pivots
+// (= prod L_kk^2) and the first non-positive pivot (1-based, 0 = none).
+// Right-looking: the row operations that reduce A to I are applied to an identity.
+__device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
+                                            double& t0, double& t1, double& pivprod, int& badk) {
+  t0 = (L.g == 2 * L.t) ? 1.0 : 0.0;
+  t1 = (L.g == 2 * L.t + 1) ? 1.0 : 0.0;
+  pivprod = 1.0; badk = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int kc = k >> 1;
+    const double ak = (k & 1) ? a1 : a0;                            // A[g][k] on lanes with t == kc
+    const double d = __shfl_sync(FULL, ak, k * 4 + kc);             // pivot
+    if (!(d > 0.0) && badk == 0) badk = k + 1;
+    const double rinv = rsqrt(d);
+    pivprod *= d;
+    const double lg = __shfl_sync(FULL, ak, L.g * 4 + kc) * rinv;            // L[g][k]
+    const double lc0 = __shfl_sync(FULL, ak, (2 * L.t) * 4 + kc) * rinv;     // L[2t][k]
+    const double lc1 = __shfl_sync(FULL, ak, (2 * L.t + 1) * 4 + kc) * rinv; // L[2t+1][k]
+    a0 = fma(-lg, lc0, a0); a1 = fma(-lg, lc1, a1);
+    const double tk0 = __shfl_sync(FULL, t0, k * 4 + L.t) * rinv;   // row k of T, scaled
+    const double tk1 = __shfl_sync(FULL, t1, k * 4 + L.t) * rinv;
+    if (L.g == k) { t0 = tk0; t1 = tk1; }
+    else if (L.g > k) { t0 = fma(-lg, tk0, t0); t1 = fma(-lg, tk1, t1); }
+  }
+}
+
+template <int TASK> __host__ __device__ constexpr int n_vec() {
+  return TASK == TASK_LL ? 1 : (TASK == TASK_PREDICT ? 3 : (TASK == TASK_LOO ? 6 : 0));
+}
+
+// ---------------------------------------------------------------------------------------
+template <int DIM, int TASK, int NB_MAX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+small_gp_kernel(const SmallArgs a, const int nbm) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Lane L(lane);
+  const Cov cov = a.cov;
+  constexpr int NT = WARPS * 32;
+  constexpr int KMAX = (NB_MAX - 1 + WARPS - 1) / WARPS;   // L^-1 row: tiles per warp
+
+  const int ld = 8 * nbm;
+  double* tiles = smem;                                   // nbm(nbm+1)/2 tiles
+  double* px = tiles + ((nbm * (nbm + 1)) >> 1) * TILE;   // coordinates, DIM * ld
+  double* noise = px + DIM * ld;                          // y_err^2 + floor^2 + nugget^2
+  double* vr = noise + ld;                                // r = y - y0  (LL: overwritten by z)
+  double* vz = vr + ld;                                   // z = L^-1 r
+  double* va = vz + ld;                                   // alpha = K^-1 r
+  double* vd = va + ld;                                   // diag(K^-1)
+  double* v1 = vd + ld;                                   // L^-1 1
+  double* vu = v1 + ld;                                   // K^-1 1
+  __shared__ double s_scal[4];                            // logdet, quad, sum r
+  __shared__ int s_bad;
+
+  const int split = (TASK == TASK_PREDICT) ? a.split : 1;
+  const int64_t n_work = a.n_obj * split;
+
+  for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int64_t oi = w / split;
+    const int part = (int)(w - oi * split);
+    const int64_t b = a.order ? a.order[oi] : oi;
+    const int64_t o0 = a.off[b];
+    const int n = (int)(a.off[b + 1] - o0);
+    const int nb = (n + 7) >> 3;
+
+    // ---------------- stage the object
+    cta_sync<WARPS>();                                    // previous object fully consumed
+    double rsum = 0.0;
+    for (int i = tid; i < 8 * nb; i += NT) {
+      const bool in = i < n;
+      if (DIM == 1) {
+        px[i] = in ? a.x[o0 + i] : 0.0;
+      } else {
+        px[i] = in ? a.x[2 * (o0 + i)] : 0.0;
+        px[ld + i] = in ? a.x[2 * (o0 + i) + 1] : 0.0;
+      }
+      const double ye = (in && a.yerr) ? a.yerr[o0 + i] : 0.0;
+      noise[i] = ye * ye + cov.noise_const;
+      if (TASK != TASK_MATRICES) {
+        const double r = in ? (a.y[o0 + i] - (a.y0 ? a.y0[o0 + i] : 0.0)) : 0.0;
+        vr[i] = r; rsum += r;
+      }
+    }
+    if (tid == 0) { s_scal[0] = 0.0; s_scal[1] = 0.0; s_scal[2] = 0.0; s_bad = 0; }
+    cta_sync<WARPS>();
+    if (TASK == TASK_LOO && a.loo_mode == 1) {
+      rsum = red_warp(rsum);
+      if (lane == 0) atomicAdd(&s_scal[2], rsum);
+    }
+
+    // ---------------- left-looking block Cholesky; slot(J,J) receives T_J = L_JJ^-1
+    for (int J = 0; J < nb; ++J) {
+      for (int I = J + warp; I < nb; I += WARPS) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int P = 0; P < J; ++P) {
+          const double2 fa = ld_frag(tiles, slot(I, P), L);
+          const double2 fb = ld_frag(tiles, slot(J, P), L);
+          dmma(s0, s1, fa.x, fb.x); dmma(s0, s1, fa.y, fb.y);
+        }
+        // K tile (I,J) in accumulator layout; rows/cols >= n pad with the identity
+        const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
+        double k0 = 0.0, k1 = 0.0;
+        {
+          const double xi = px[gi], yi = (DIM == 2) ? px[ld + gi] : 0.0;
+          if (gi < n && cj < gi) k0 = rbf<DIM>(cov, cov.amp_auto, xi, yi, px[cj], (DIM == 2) ? px[ld + cj] : 0.0);
+          if (gi < n && cj + 1 < gi) k1 = rbf<DIM>(cov, cov.amp_auto, xi, yi, px[cj + 1], (DIM == 2) ? px[ld + cj + 1] : 0.0);
+          if (cj == gi) k0 = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
+          if (cj + 1 == gi) k1 = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
+        }
+        k0 -= s0; k1 -= s1;
+        if (I == J) {                                     // warp 0
+          double t0, t1, piv; int badk;
+          diag_factor(k0, k1, L, t0, t1, piv, badk);
+          st_acc(tiles, slot(J, J), L, t0, t1);
+          if (lane == 0) {
+            s_scal[0] += log(piv);
+            if (badk && s_bad == 0) s_bad = 8 * J + badk;
+          }
+        } else {
+          st_acc(tiles, slot(I, J), L, k0, k1);           // park C[I][J] in its own slot
+        }
+      }
+      cta_sync<WARPS>();
+      const double2 ft = ld_frag(tiles, slot(J, J), L);
+      for (int I = J + 1 + warp; I < nb; I += WARPS) {    // L[I][J] = C[I][J] T_J^T
+        const double2 fc = ld_frag(tiles, slot(I, J), L);
+        double d0 = 0.0, d1 = 0.0;
+        dmma(d0, d1, fc.x, ft.x); dmma(d0, d1, fc.y, ft.y);
+        __syncwarp();
+        st_acc(tiles, slot(I, J), L, d0, d1);
+      }
+      cta_sync<WARPS>();
+    }
+
+    if (TASK == TASK_LL) {
+      // ---------------- z = L^-1 r by block forward substitution (warp 0), quad = |z|^2
+      if (warp == 0) {
+        double quad = 0.0;
+        for (int J = 0; J < nb; ++J) {
+          double p = 0.0;
+          for (int P = 0; P < J; ++P) {
+            const double2 f = ld_frag(tiles, slot(J, P), L);
+            p = fma(f.x, vr[8 * P + L.t], p); p = fma(f.y, vr[8 * P + 4 + L.t], p);
+          }
+          const double wv = vr[8 * J + L.g] - red_t(p);
+          const double2 f = ld_frag(tiles, slot(J, J), L);
+          double q = f.x * __shfl_sync(FULL, wv, L.t * 4) + f.y * __shfl_sync(FULL, wv, (4 + L.t) * 4);
+          q = red_t(q);
+          if (L.t == 0) { vr[8 * J + L.g] = q; quad = fma(q, q, quad); }
+          __syncwarp();
+        }
+        quad = red_warp(quad);
+        if (lane == 0) {
+          const int bad = s_bad;
+          a.info[b] = bad;
+          a.ll[b] = bad ? nan("") : -0.5 * (quad + s_scal[0] + n * LOG_2PI);
+        }
+      }
+      continue;
+    }
+
+    // ---------------- L^-1, row by row, in place (slot(I,J) <- L^-1[I][J]);
+    // L^-1[I][J] = -T_I * sum_{P=J..I-1} L[I][P] L^-1[P][J]
+    for (int I = 1; I < nb; ++I) {
+      double s0[KMAX], s1[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int J = warp + k * WARPS;
+        s0[k] = 0.0; s1[k] = 0.0;
+        if (J < I) {
+          for (int P = J; P < I; ++P) {
+            const double2 fa = ld_frag(tiles, slot(I, P), L);
+            const double2 fb = ld_fragT(tiles, slot(P, J), L);
+            dmma(s0[k], s1[k], fa.x, fb.x); dmma(s0[k], s1[k], fa.y, fb.y);
+          }
+        }
+      }
+      cta_sync<WARPS>();                                  // every read of row I of L is done
+      const double2 ft = ld_frag(tiles, slot(I, I), L);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int J = warp + k * WARPS;
+        if (J < I) {
+          st_acc(tiles, slot(I, J), L, s0[k], s1[k]);
+          __syncwarp();
+          const double2 fs = ld_fragT(tiles, slot(I, J), L);
+          double d0 = 0.0, d1 = 0.0;
+          dmma(d0, d1, ft.x, fs.x); dmma(d0, d1, ft.y, fs.y);
+          __syncwarp();
+          st_acc(tiles, slot(I, J), L, -d0, -d1);
+        }
+      }
+      cta_sync<WARPS>();
+    }
+
+    if (TASK == TASK_MATRICES) {
+      const int bad = s_bad;
+      if (tid == 0) a.info[b] = bad;
+      const int64_t mo = a.moff[b];
+      if (a.kmat) {
+        for (int e = tid; e < n * n; e += NT) {
+          const int i = e / n, j = e - i * n;
+          double v;
+          if (i == j) v = cov.amp_auto + noise[i];
+          else v = rbf<DIM>(cov, cov.amp_auto, px[i], (DIM == 2) ? px[ld + i] : 0.0, px[j], (DIM == 2) ? px[ld + j] : 0.0);
+          a.kmat[mo + e] = v;
+        }
+      }
+      if (a.kinv) {       // K^-1 = L^-T L^-1: tile (I,J) = sum_{P>=I} Linv[P][I]^T Linv[P][J]
+        int q = 0;
+        for (int I = 0; I < nb; ++I)
+          for (int J = 0; J <= I; ++J, ++q) {
+            if (q % WARPS != warp) continue;
+            double c0 = 0.0, c1 = 0.0;
+            for (int P = I; P < nb; ++P) {
+              const double2 fa = ld_fragT(tiles, slot(P, I), L);
+              const double2 fb = ld_fragT(tiles, slot(P, J), L);
+              dmma(c0, c1, fa.x, fb.x); dmma(c0, c1, fa.y, fb.y);
+            }
+            if (bad) { c0 = nan(""); c1 = c0; }
+            const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
+            if (gi < n) {
+              if (cj < n) { a.kinv[mo + (int64_t)gi * n + cj] = c0; a.kinv[mo + (int64_t)cj * n + gi] = c0; }
+              if (cj + 1 < n) { a.kinv[mo + (int64_t)gi * n + cj + 1] = c1; a.kinv[mo + (int64_t)(cj + 1) * n + gi] = c1; }
+            }
+          }
+      }
+      continue;
+    }
+
+    // ---------------- z = L^-1 r  (and L^-1 1), then alpha = L^-T z, d = colnorm^2(L^-1), u = L^-T(L^-1 1)
+    const bool want_u = (TASK == TASK_LOO) && (a.loo_mode == 1);
+    for (int I = warp; I < nb; I += WARPS) {
+      double p = 0.0, p1 = 0.0;
+      for (int J = 0; J <= I; ++J) {
+        const double2 f = ld_frag(tiles, slot(I, J), L);
+        p = fma(f.x, vr[8 * J + L.t], p); p = fma(f.y, vr[8 * J + 4 + L.t], p);
+        if (want_u) {                                     // padded columns multiply exact zeros of L^-1
+          p1 += f.x; p1 += f.y;
+        }
+      }
+      p = red_t(p);
+      if (L.t == 0) vz[8 * I + L.g] = p;
+      if (want_u) { p1 = red_t(p1); if (L.t == 0) v1[8 * I + L.g] = (8 * I + L.g < n) ? p1 : 0.0; }
+    }
+    cta_sync<WARPS>();
+    for (int J = warp; J < nb; J += WARPS) {
+      double pa0 = 0.0, pa1 = 0.0, pd0 = 0.0, pd1 = 0.0, pu0 = 0.0, pu1 = 0.0;
+      for (int I = J; I < nb; ++I) {
+        const double2 f = ld_frag(tiles, slot(I, J), L);
+        const double zi = vz[8 * I + L.g];
+        pa0 = fma(f.x, zi, pa0); pa1 = fma(f.y, zi, pa1);
+        if (TASK == TASK_LOO) {
+          // rows >= n of L^-1 are identity rows: keep them out of the column norms
+          const bool in = 8 * I + L.g < n;
+          pd0 = in ? fma(f.x, f.x, pd0) : pd0; pd1 = in ? fma(f.y, f.y, pd1) : pd1;
+          if (want_u) { const double ui = v1[8 * I + L.g]; pu0 = fma(f.x, ui, pu0); pu1 = fma(f.y, ui, pu1); }
+        }
+      }
+      pa0 = red_g(pa0); pa1 = red_g(pa1);
+      if (L.g == 0) { va[8 * J + L.t] = pa0; va[8 * J + 4 + L.t] = pa1; }
+      if (TASK == TASK_LOO) {
+        pd0 = red_g(pd0); pd1 = red_g(pd1);
+        if (L.g == 0) { vd[8 * J + L.t] = pd0; vd[8 * J + 4 + L.t] = pd1; }
+        if (want_u) {
+          pu0 = red_g(pu0); pu1 = red_g(pu1);
+          if (L.g == 0) { vu[8 * J + L.t] = pu0; vu[8 * J + 4 + L.t] = pu1; }
+        }
+      }
+    }
+    cta_sync<WARPS>();
+    const int bad = s_bad;
+    if (tid == 0 && part == 0) a.info[b] = bad;
+
+    if (TASK == TASK_LOO) {
+      // ---------------- closed-form leave-one-out (pull.py:66-94)
+      const double rho = cov.amp_cross / cov.amp_auto;
+      const double amp_star = cov.amp_auto + cov.nugget2;
+      const double rs = s_scal[2];
+      for (int i = tid; i < n; i += NT) {
+        const double d = vd[i], r = vr[i];
+        const double yv = a.y[o0 + i];
+        const double m = a.y0 ? a.y0[o0 + i] : 0.0;
+        const double ye = a.yerr ? a.yerr[o0 + i] : 0.0;
+        double pr = m + rho * (r - va[i] / d);
+        if (want_u) {
+          const double delta = (rs - r) / (double)(n - 1);
+          pr += delta - delta * rho * (1.0 - vu[i] / d);
+        }
+        double pv = fabs(amp_star - rho * rho * (cov.amp_auto + noise[i] - 1.0 / d));
+        double res = pr - yv;
+        double pl = res / sqrt(ye * ye + pv + cov.nugget2);
+        if (bad) { pr = nan(""); pv = pr; res = pr; pl = pr; }
+        if (a.pred) a.pred[o0 + i] = pr;
+        if (a.pvar) a.pvar[o0 + i] = pv;
+        if (a.resid) a.resid[o0 + i] = res;
+        if (a.pull) a.pull[o0 + i] = pl;
+      }
+      continue;
+    }
+
+    if (TASK == TASK_PREDICT) {
+      // ---------------- grid points in blocks of 8: v = L^-1 h, mean = h.alpha + y0*, var = amp* - |v|^2
+      const int64_t g0 = a.goff ? a.goff[b] : 0;
+      const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
+      const int64_t out0 = a.goff ? g0 : b * a.m_shared;
+      const int64_t n_rb = (m_pts + 7) >> 3;
+      const double amp_star = cov.amp_auto + cov.nugget2;
+      for (int64_t rb = (int64_t)part * WARPS + warp; rb < n_rb; rb += (int64_t)split * WARPS) {
+        const int64_t mi = 8 * rb + L.g;
+        const bool live = mi < m_pts;
+        double gx = 0.0, gy = 0.0;
+        if (live) {
+          if (DIM == 1) gx = a.xnew[g0 + mi];
+          else { gx = a.xnew[2 * (g0 + mi)]; gy = a.xnew[2 * (g0 + mi) + 1]; }
+        }
+        double acc0[NB_MAX], acc1[NB_MAX];
+#pragma unroll
+        for (int J = 0; J < NB_MAX; ++J) { acc0[J] = 0.0; acc1[J] = 0.0; }
+        double pm = 0.0;
+#pragma unroll
+        for (int P = 0; P < NB_MAX; ++P) {
+          if (P < nb) {
+            const int c0 = 8 * P + L.t, c1 = c0 + 4;
+            double h0 = 0.0, h1 = 0.0;                    // A fragment of the cross-covariance block
+            if (live && c0 < n) h0 = rbf<DIM>(cov, cov.amp_cross, gx, gy, px[c0], (DIM == 2) ? px[ld + c0] : 0.0);
+            if (live && c1 < n) h1 = rbf<DIM>(cov, cov.amp_cross, gx, gy, px[c1], (DIM == 2) ? px[ld + c1] : 0.0);
+            pm = fma(h0, va[c0], pm); pm = fma(h1, va[c1], pm);
+#pragma unroll
+            for (int J = P; J < NB_MAX; ++J) {
+              if (J < nb) {
+                const double2 fb = ld_frag(tiles, slot(J, P), L);
+                dmma(acc0[J], acc1[J], h0, fb.x); dmma(acc0[J], acc1[J], h1, fb.y);
+              }
+            }
+          }
+        }
+        double vv = 0.0;
+#pragma unroll
+        for (int J = 0; J < NB_MAX; ++J) { vv = fma(acc0[J], acc0[J], vv); vv = fma(acc1[J], acc1[J], vv); }
+        pm = red_t(pm); vv = red_t(vv);
+        if (live && L.t == 0) {
+          double mean = pm + (a.new_y0 ? a.new_y0[out0 + mi] : 0.0);
+          double var = amp_star - vv;
+          if (bad) { mean = nan(""); var = mean; }
+          a.mean[out0 + mi] = mean;
+          if (a.var) a.var[out0 + mi] = var;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+template <int DIM, int TASK, int NB_MAX, int WARPS>
+int launch_one(int nbm, const SmallArgs& a, cudaStream_t stream) {
+  auto kern = small_gp_kernel<DIM, TASK, NB_MAX, WARPS>;
+  const size_t smem = small_smem_bytes((Task)TASK, DIM, nbm);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+  if (e != cudaSuccess) return (int)e;
+  if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
+  const int64_t n_work = a.n_obj * (TASK == TASK_PREDICT ? a.split : 1);
+  int64_t grid = (int64_t)sm_count * per_sm;
+  if (grid > n_work) grid = n_work;
+  if (grid < 1) return 0;
+  kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(a, nbm);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <int DIM, int TASK>
+int launch_cfg(int nbm, const SmallArgs& a, cudaStream_t stream) {
+  if (nbm <= 8) return launch_one<DIM, TASK, 8, 1>(nbm, a, stream);
+  if (nbm <= 16) return launch_one<DIM, TASK, 16, 4>(nbm, a, stream);
+  return launch_one<DIM, TASK, 28, 4>(nbm, a, stream);
+}
+
+template <int DIM>
+int launch_task(Task task, int nbm, const SmallArgs& a, cudaStream_t stream) {
+  switch (task) {
+    case TASK_LL: return launch_cfg<DIM, TASK_LL>(nbm, a, stream);
+    case TASK_PREDICT: return launch_cfg<DIM, TASK_PREDICT>(nbm, a, stream);
+    case TASK_LOO: return launch_cfg<DIM, TASK_LOO>(nbm, a, stream);
+    case TASK_MATRICES: return launch_cfg<DIM, TASK_MATRICES>(nbm, a, stream);
+  }
+  return (int)cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 ceiling probes (the roofline denominator is measured on the box, not assumed).
+__global__ void peak_dfma(double* out, int iters, double a, double b) {
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += acc[i];
+  if (s == 123.456) out[0] = s;
+}
+__global__ void peak_dmma(double* out, int iters, double a, double b) {
+  double c0[8], c1[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c0[i] = threadIdx.x; c1[i] = i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c0[i] + c1[i];
+  if (s == 123.456) out[0] = s;
+}
+
+}  // namespace
+
+size_t small_smem_bytes(Task task, int dim, int nb) {
+  const int nv = task == TASK_LL ? 1 : (task == TASK_PREDICT ? 3 : (task == TASK_LOO ? 6 : 0));
+  size_t doubles = (size_t)((nb * (nb + 1)) / 2) * TILE + (size_t)(dim + 1 + nv) * 8 * nb;
+  return doubles * sizeof(double);
+}
+
+int launch_small(Task task, int dim, int max_n, const SmallArgs& a, cudaStream_t stream) {
+  const int nbm = max_n < 1 ? 1 : (max_n + 7) / 8;
+  if (nbm > 28) return (int)cudaErrorInvalidValue;
+  return dim == 1 ? launch_task<1>(task, nbm, a, stream) : launch_task<2>(task, nbm, a, stream);
+}
+
+int measure_fp64_peak(int kind, double* tflops) {
+  int dev, sms;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* d;
+  cudaError_t e = cudaMalloc(&d, 64);
+  if (e != cudaSuccess) return (int)e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 8192, grid = sms * 4, threads = 256;
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    if (kind == 0) peak_dfma<<<grid, threads>>>(d, iters, 1.0000001, 1e-9);
+    else peak_dmma<<<grid, threads>>>(d, iters, 1e-3, 1e-3);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep && ms < best) best = ms;
+  }
+  count_launch(6);
+  const double fl = kind == 0 ? 2.0 * 8 * iters * (double)grid * threads
+                              : 2.0 * 256 * 8 * iters * (double)grid * (threads / 32);
+  *tflops = fl / best * 1e-9;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace cgp

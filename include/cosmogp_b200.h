@@ -1,0 +1,120 @@
+/* cosmogp_b200 -- C ABI of the B200 (sm_100a) Gaussian-process hot path.
+ *
+ * Drop-in boundary for PFLeget/cosmogp (reference citations are file:line into
+ * that repository).  The reference has no FFI; its only plugin seams are
+ *   (1) the inverse operators `svd` / `chol` bound at cosmogp/Gaussian_process.py:6-9
+ *       (svd_tmv.computeSVDInverse / computeLDLInverse if importable),
+ *   (2) the kernel callable chosen at cosmogp/Gaussian_process.py:136-154,
+ *   (3) the object API (Gaussian_process / build_pull) whose per-object Python
+ *       loops (Gaussian_process.py:207,264,304,349; pull.py:51,66) are the hot path.
+ * Each entry point below replaces one of those loops or operators for a whole
+ * batch of objects.  INTEGRATION.md shows the ctypes stubs a cosmogp maintainer
+ * would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 ok; <0 error (text via cgp_last_error());
+ *     >0 = number of objects whose covariance was not positive definite
+ *     (the LinAlgError of scipy.linalg.cholesky at cosmogp/inv_matrix.py:23);
+ *     their info[] holds the 1-based failing pivot and their outputs are NaN.
+ *   - "_dev" functions take DEVICE pointers and a cudaStream_t (as void*); they
+ *     enqueue work and return without synchronising unless stated.
+ *     "_host" functions take HOST pointers, do H2D + compute + D2H and return
+ *     when the outputs are valid.
+ *   - ragged batches are CSR: off[n_obj+1] (int64) into x / y / y0 / y_err.
+ *     "_dev" functions also take max_n, the largest object size in the batch (the
+ *     host picks the kernel configuration from it); pass 0 to have the library read
+ *     off[] back from the device (this synchronises the stream).
+ *     x holds dim doubles per point (dim = 1: RBF1D, dim = 2: RBF2D, xy interleaved).
+ *     y0 and y_err may be NULL (zeros), like the reference defaults
+ *     (Gaussian_process.py:161-169,187).
+ *   - hyp = [sigma, l] (dim 1, cosmogp/kernel.py:25-77) or
+ *           [sigma, l_x, l_y, l_xy] (dim 2, cosmogp/kernel.py:80-155).
+ *   - flags: CGP_AMP_ON_AUTOCOV applies sigma^2 to the 2D auto-covariance; the
+ *     default (0) reproduces HEAD, which omits it (kernel.py:146-148).
+ *   - all arithmetic is IEEE float64.
+ */
+#ifndef COSMOGP_B200_H
+#define COSMOGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGP_AMP_ON_AUTOCOV 1u      /* opt-in fix of the 2D sigma^2 omission */
+
+#define CGP_SMALL_MAX_N 224        /* largest object the shared-memory path takes */
+
+/* leave-one-out mean handling (cosmogp/pull.py:43-102) */
+#define CGP_LOO_PLAIN    0         /* pred = m + loo(y - m); m may be NULL (modes A, C) */
+#define CGP_LOO_RECENTER 1         /* diff re-estimated on the N-1 kept points (modes B, D) */
+
+/* ---- library ------------------------------------------------------------ */
+int         cgp_version(void);
+const char* cgp_last_error(void);
+/* number of visible CUDA devices, <0 on error */
+int         cgp_device_count(void);
+/* measured FP64 ceiling of the current device in TFLOP/s: kind 0 = DFMA, 1 = DMMA (m8n8k4). */
+int         cgp_fp64_peak(int kind, double* tflops);
+/* kernels launched by this library since load (all streams); bench.py reports the delta. */
+int64_t     cgp_launch_count(void);
+
+/* ---- log-likelihood: replaces the loop of Gaussian_process.compute_log_likelihood
+ *      (cosmogp/Gaussian_process.py:191-213) over log_likelihood_gp (:13-75) with
+ *      svd_method=False (Cholesky, inv_matrix.py:21-31).
+ *      ll_obj[n_obj]: per-object log-likelihood; info[n_obj]. */
+int cgp_ll_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                       const double* x, const double* y, const double* y0, const double* y_err,
+                       const double* hyp, double nugget, double floor, unsigned flags,
+                       double* ll_obj, int* info, void* stream);
+/* host buffers; *ll_sum = sum over objects in index order (Gaussian_process.py:205-213). */
+int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
+                        const double* x, const double* y, const double* y0, const double* y_err,
+                        const double* hyp, double nugget, double floor, unsigned flags,
+                        double* ll_obj, int* info, double* ll_sum);
+
+/* ---- prediction: replaces Gaussian_process.get_prediction + get_covariance_matrix
+ *      (cosmogp/Gaussian_process.py:270-361).
+ *      Grid: if goff == NULL the m_shared points of xnew are shared by all objects
+ *      (new_binning given) and outputs are (n_obj, m_shared) row-major; otherwise
+ *      goff[n_obj+1] is a CSR into xnew / new_y0 / mean / var (new_binning=None).
+ *      new_y0 (mean function on the grid, may be NULL) has the output layout.
+ *      mean = H K^-1 (y - y0) + new_y0                      (:332-335)
+ *      var  = diag(K(x*,x*) + nugget^2 - H K^-1 H^T)         (:356-361), may be NULL. */
+int cgp_predict_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                            const double* x, const double* y, const double* y0, const double* y_err,
+                            const double* hyp, double nugget, double floor, unsigned flags,
+                            const double* xnew, const int64_t* goff, int64_t m_shared,
+                            const double* new_y0, double* mean, double* var, int* info, void* stream);
+int cgp_predict_batched_host(int64_t n_obj, const int64_t* off, int dim,
+                             const double* x, const double* y, const double* y0, const double* y_err,
+                             const double* hyp, double nugget, double floor, unsigned flags,
+                             const double* xnew, const int64_t* goff, int64_t m_shared,
+                             const double* new_y0, double* mean, double* var, int* info);
+
+/* ---- leave-one-out pulls: replaces build_pull.compute_pull (cosmogp/pull.py:43-102)
+ *      by the closed form on diag(K^-1).  m (template mean incl. any fixed diff) may be
+ *      NULL.  Outputs (each sum-of-N doubles, any may be NULL): pred, pred_var, pull, resid. */
+int cgp_loo_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                        const double* x, const double* y, const double* m, const double* y_err,
+                        const double* hyp, double nugget, double floor, unsigned flags, int mode,
+                        double* pred, double* pred_var, double* pull, double* resid,
+                        int* info, void* stream);
+int cgp_loo_batched_host(int64_t n_obj, const int64_t* off, int dim,
+                         const double* x, const double* y, const double* m, const double* y_err,
+                         const double* hyp, double nugget, double floor, unsigned flags, int mode,
+                         double* pred, double* pred_var, double* pull, double* resid, int* info);
+
+/* ---- matrices for the attribute surface (kernel_matrix, inv_kernel_matrix:
+ *      Gaussian_process.py:256-267, 319-325).  moff[n_obj+1]: CSR into the outputs in
+ *      doubles (object b is an N_b x N_b row-major block).  kmat / kinv may be NULL. */
+int cgp_matrices_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                             const double* x, const double* y_err,
+                             const double* hyp, double nugget, double floor, unsigned flags,
+                             const int64_t* moff, double* kmat, double* kinv, int* info, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSMOGP_B200_H */

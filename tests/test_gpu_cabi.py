@@ -1,0 +1,295 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI with host buffers,
+against (a) fixtures produced by the real reference and (b) the pinned oracle on
+seeded inputs.  Tolerance: relative 1e-9 (BASELINE.json north_star) on
+log-likelihood, predictions, variances and pulls, with a small absolute floor where
+a quantity passes through zero."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import assert_close, golden, split
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def L():
+    from cosmogp_b200 import _lib
+    _lib.require_device()
+    return _lib
+
+
+def csr(arrs):
+    off = np.zeros(len(arrs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(a) for a in arrs])
+    return np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a in arrs])), off
+
+
+def run_ll(L, xs, ys, y0s, yes, hyp, nugget, dim=1, floor=0.0, flags=0):
+    x, off = csr(xs); y, _ = csr(ys)
+    y0 = csr(y0s)[0] if y0s is not None else None
+    ye = csr(yes)[0] if yes is not None else None
+    b = len(xs)
+    ll = np.full(b, -7.0); info = np.full(b, -1, dtype=np.int32); tot = C.c_double(0)
+    hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+    rc = L.lib().cgp_ll_batched_host(b, L.hptr(off), dim, L.hptr(x), L.hptr(y), L.hptr(y0), L.hptr(ye),
+                                     L.hptr(hyp), nugget, floor, flags, L.hptr(ll), L.hptr(info), C.byref(tot))
+    L.check(rc, "ll")
+    return ll, info, tot.value, rc
+
+
+def run_predict(L, xs, ys, y0s, yes, hyp, nugget, grid, new_y0=None, dim=1, goff=None, want_var=True, flags=0):
+    x, off = csr(xs); y, _ = csr(ys)
+    y0 = csr(y0s)[0] if y0s is not None else None
+    ye = csr(yes)[0] if yes is not None else None
+    b = len(xs)
+    grid = np.ascontiguousarray(grid, dtype=np.float64)
+    m = len(grid) if goff is None else 0
+    nout = b * m if goff is None else int(goff[-1])
+    mean = np.full(nout, -7.0); var = np.full(nout, -7.0) if want_var else None
+    info = np.full(b, -1, dtype=np.int32)
+    hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+    ny0 = None if new_y0 is None else np.ascontiguousarray(new_y0, dtype=np.float64)
+    rc = L.lib().cgp_predict_batched_host(b, L.hptr(off), dim, L.hptr(x), L.hptr(y), L.hptr(y0), L.hptr(ye),
+                                          L.hptr(hyp), nugget, 0.0, flags, L.hptr(grid),
+                                          None if goff is None else L.hptr(goff), m, L.hptr(ny0),
+                                          L.hptr(mean), L.hptr(var), L.hptr(info))
+    L.check(rc, "predict")
+    if goff is None:
+        return mean.reshape(b, m), (var.reshape(b, m) if want_var else None), info
+    return mean, var, info
+
+
+def run_loo(L, xs, ys, ms, yes, hyp, nugget, mode=0, dim=1):
+    x, off = csr(xs); y, _ = csr(ys)
+    m = csr(ms)[0] if ms is not None else None
+    ye = csr(yes)[0] if yes is not None else None
+    b = len(xs); npt = int(off[-1])
+    out = [np.full(npt, -7.0) for _ in range(4)]
+    info = np.full(b, -1, dtype=np.int32)
+    hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+    rc = L.lib().cgp_loo_batched_host(b, L.hptr(off), dim, L.hptr(x), L.hptr(y), L.hptr(m), L.hptr(ye),
+                                      L.hptr(hyp), nugget, 0.0, 0, mode, *[L.hptr(o) for o in out], L.hptr(info))
+    L.check(rc, "loo")
+    return out + [info]
+
+
+# --------------------------------------------------------------------------- golden fixtures
+def test_kat_1d(L):
+    g = golden("kat_1d")
+    ll, info, tot, rc = run_ll(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], float(g["nugget"]))
+    assert rc == 0 and info[0] == 0
+    assert_close(ll[0], g["ll_chol"], RTOL); assert_close(tot, g["ll_chol"], RTOL)
+    mean, var, _ = run_predict(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], float(g["nugget"]), g["grid"])
+    assert_close(mean[0], g["mean"], RTOL); assert_close(var[0], np.diag(g["cov"]), RTOL)
+    pred, pvar, pull, resid, _ = run_loo(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], float(g["nugget"]))
+    assert_close(pull, g["pull"], RTOL, 1e-13); assert_close(pred, g["pred"], RTOL, 1e-13)
+    assert_close(resid, g["resid"], RTOL, 1e-13)
+
+
+def test_kat_2d(L):
+    g = golden("kat_2d")
+    nug = float(g["nugget"])
+    ll, info, _, _ = run_ll(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], nug, dim=2)
+    assert info[0] == 0
+    assert_close(ll[0], g["ll_chol"], RTOL)
+    mean, var, _ = run_predict(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], nug, g["grid"], dim=2)
+    assert_close(mean[0], g["mean"], RTOL); assert_close(var[0], np.diag(g["cov"]), RTOL)
+    pred, _, pull, resid, _ = run_loo(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], nug, dim=2)
+    assert_close(pull, g["pull"], RTOL, 1e-12); assert_close(pred, g["pred"], RTOL, 1e-12)
+
+
+def test_c1_single_light_curve(L):
+    """BASELINE config 1: N=50 epochs, predict on a 500-point grid."""
+    g = golden("c1_single")
+    nug = float(g["nugget"])
+    ll, info, _, _ = run_ll(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], nug)
+    assert info[0] == 0
+    assert_close(ll[0], g["ll_chol"], RTOL)
+    mean, var, _ = run_predict(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], nug, g["grid"])
+    assert_close(mean[0], g["mean"], RTOL, 1e-12); assert_close(var[0], g["cov_diag"], RTOL, 1e-13)
+    _, _, pull, resid, _ = run_loo(L, [g["x"]], [g["y"]], None, [g["y_err"]], g["hyp"], nug)
+    assert_close(pull, g["pull"], RTOL, 1e-11); assert_close(resid, g["resid"], RTOL, 1e-12)
+
+
+def test_ragged_1d_shared_mean(L):
+    g = golden("ragged_1d")
+    off, hyp, nug = g["off"], g["hyp"], float(g["nugget"])
+    xs, ys, yes, y0s = (split(g[k], off) for k in ("x", "y", "y_err", "y0"))
+    ll, info, tot, rc = run_ll(L, xs, ys, y0s, yes, hyp, nug)
+    assert rc == 0 and not info.any()
+    assert_close(ll, g["ll_obj"], RTOL); assert_close(tot, g["ll_sum"], RTOL)
+    _, _, tot7, _ = run_ll(L, xs, ys, y0s, yes, hyp, 0.07)
+    assert_close(tot7, g["ll_sum_nugget007"], RTOL)
+    ny0 = np.array([O.return_mean_1d(ys[i], xs[i], g["mean_y"], g["mean_x"], new_x=g["grid"]) for i in range(len(xs))])
+    mean, var, _ = run_predict(L, xs, ys, y0s, yes, hyp, nug, g["grid"], new_y0=ny0)
+    assert_close(mean, g["mean"], RTOL); assert_close(var, g["var"], RTOL, 1e-13)
+    # own-epoch grid (new_binning=None) through the CSR grid path
+    m0, v0, _ = run_predict(L, xs[:1], ys[:1], y0s[:1], yes[:1], hyp, 0.05, xs[0], new_y0=y0s[0],
+                            goff=np.array([0, len(xs[0])], dtype=np.int64))
+    assert_close(m0, g["own_mean0"], RTOL); assert_close(v0, np.diag(g["own_cov0"]), RTOL, 1e-13)
+    # pulls: mode B (mean, diff None -> recentred) and mode C (diff given -> plain)
+    tmpl = [O.return_mean_1d(ys[i], xs[i], g["mean_y"], g["mean_x"], diff=0.0) for i in range(len(xs))]
+    pred, _, pull, resid, _ = run_loo(L, xs, ys, tmpl, yes, hyp, 0.05, mode=1)
+    assert_close(pull, g["pullB"], 1e-8, 1e-11); assert_close(pred, g["predB"], RTOL, 1e-11)
+    mc = [tmpl[i] + g["diff"][i] for i in range(len(xs))]
+    pred, _, pull, resid, _ = run_loo(L, xs, ys, mc, yes, hyp, 0.05, mode=0)
+    assert_close(pull, g["pullC"], 1e-8, 1e-11); assert_close(pred, g["predC"], RTOL, 1e-11)
+
+
+def test_pulls_modes_a_d(L):
+    g = golden("pulls_1d")
+    hyp, nug = g["hyp"], float(g["nugget"])
+    pred, _, pull, resid, info = run_loo(L, list(g["x"]), list(g["y"]), None, list(g["y_err"]), hyp, nug)
+    assert not info.any()
+    assert_close(pull, g["pullA"], RTOL, 1e-12); assert_close(pred, g["predA"].ravel(), RTOL, 1e-12)
+    assert_close(resid, g["residA"], RTOL, 1e-12)
+    sticky = np.ones(40) * np.mean(g["yD"][0])
+    pred, _, pull, _, _ = run_loo(L, [g["xD"]] * 3, list(g["yD"]), [sticky] * 3, list(g["y_err"][:3]), hyp, nug, mode=1)
+    assert_close(pull, g["pullD"], 1e-8, 1e-11); assert_close(pred, g["predD"].ravel(), RTOL, 1e-11)
+
+
+def test_batch_2d(L):
+    g = golden("batch_2d")
+    off, hyp, nug = g["off"], g["hyp"], float(g["nugget"])
+    xs, ys, yes = split(g["x"], off), split(g["y"], off), split(g["y_err"], off)
+    ll, info, tot, _ = _ll2d(L, xs, ys, yes, hyp, nug)
+    assert not info.any()
+    assert_close(ll, g["ll_obj"], RTOL); assert_close(tot, g["ll_sum"], RTOL)
+
+
+def _ll2d(L, xs, ys, yes, hyp, nug):
+    b = len(xs)
+    off = np.zeros(b + 1, dtype=np.int64); off[1:] = np.cumsum([len(v) for v in ys])
+    x = np.ascontiguousarray(np.concatenate(xs), dtype=np.float64)      # (sumN, 2) row-major = interleaved
+    y = np.ascontiguousarray(np.concatenate(ys)); ye = np.ascontiguousarray(np.concatenate(yes))
+    ll = np.zeros(b); info = np.zeros(b, dtype=np.int32); tot = C.c_double(0)
+    hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+    rc = L.lib().cgp_ll_batched_host(b, L.hptr(off), 2, L.hptr(x), L.hptr(y), None, L.hptr(ye), L.hptr(hyp), nug, 0.0, 0,
+                                     L.hptr(ll), L.hptr(info), C.byref(tot))
+    L.check(rc, "ll2d")
+    return ll, info, tot.value, rc
+
+
+def test_batch_2d_predict_and_pulls(L):
+    g = golden("batch_2d")
+    off, hyp, nug = g["off"], g["hyp"], float(g["nugget"])
+    xs, ys, yes = split(g["x"], off), split(g["y"], off), split(g["y_err"], off)
+    b = 3
+    x = np.ascontiguousarray(np.concatenate(xs)); y = np.concatenate(ys); ye = np.concatenate(yes)
+    grid = np.ascontiguousarray(g["grid"]); m = len(grid)
+    mean = np.zeros(b * m); var = np.zeros(b * m); info = np.zeros(b, dtype=np.int32)
+    hp = np.ascontiguousarray(hyp)
+    rc = L.lib().cgp_predict_batched_host(b, L.hptr(off), 2, L.hptr(x), L.hptr(y), None, L.hptr(ye), L.hptr(hp), nug, 0.0, 0,
+                                          L.hptr(grid), None, m, None, L.hptr(mean), L.hptr(var), L.hptr(info))
+    L.check(rc, "predict2d")
+    assert_close(mean.reshape(b, m), g["mean"], RTOL, 1e-12); assert_close(var.reshape(b, m), g["var"], RTOL, 1e-12)
+    o2 = np.array([0, len(ys[2])], dtype=np.int64)
+    x2 = np.ascontiguousarray(xs[2]); outs = [np.zeros(len(ys[2])) for _ in range(4)]
+    rc = L.lib().cgp_loo_batched_host(1, L.hptr(o2), 2, L.hptr(x2), L.hptr(np.ascontiguousarray(ys[2])), None,
+                                      L.hptr(np.ascontiguousarray(yes[2])), L.hptr(hp), nug, 0.0, 0, 0,
+                                      *[L.hptr(o) for o in outs], L.hptr(info))
+    L.check(rc, "loo2d")
+    assert_close(outs[2], g["pull2"], RTOL, 1e-12); assert_close(outs[0], g["pred2"], RTOL, 1e-12)
+
+
+def test_notebook_joint_ll(L):
+    """docs/notebook/1D_kernel_example_with_noise.ipynb: LL of the 100x60 batch at the fitted optimum."""
+    g = golden("notebook_with_noise")
+    _, info, tot, _ = run_ll(L, list(g["x"]), list(g["y"]), None, list(g["y_err"]), g["fit_joint"], 0.0)
+    assert not info.any()
+    assert_close(tot, g["ll_at_joint"], RTOL)
+
+
+# --------------------------------------------------------------------------- oracle on seeded inputs
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 33, 60, 64])
+def test_sizes_one_warp(L, n):
+    rng = np.random.default_rng(100 + n)
+    b = 37
+    xs = [np.sort(rng.uniform(-10, 40, n)) for _ in range(b)]
+    ys = [rng.standard_normal(n) for _ in range(b)]
+    yes = [rng.uniform(0.1, 0.3, n) for _ in range(b)]
+    y0s = [rng.standard_normal(n) * 0.1 for _ in range(b)]
+    hyp, nug = [0.7, 3.0], 0.05
+    ll, info, tot, _ = run_ll(L, xs, ys, y0s, yes, hyp, nug)
+    assert not info.any()
+    ref = [O.log_likelihood(ys[i], xs[i], hyp, nug, yes[i], y0s[i]) for i in range(b)]
+    assert_close(ll, ref, RTOL)
+    grid = np.linspace(-12, 42, 45)
+    mean, var, _ = run_predict(L, xs, ys, y0s, yes, hyp, nug, grid)
+    for i in range(0, b, 6):
+        mo, vo = O.predict(ys[i], xs[i], hyp, nug, grid, yes[i], y0s[i], full_cov=False)
+        assert_close(mean[i], mo, RTOL, 1e-12); assert_close(var[i], vo, RTOL, 1e-13)
+    if n >= 2:
+        pred, pvar, pull, resid, _ = run_loo(L, xs, ys, None, yes, hyp, nug)
+        po = [O.loo_closed_form(ys[i], xs[i], hyp, nug, yes[i]) for i in range(b)]
+        assert_close(pull, np.concatenate([p[2] for p in po]), RTOL, 1e-12)
+        assert_close(pvar, np.concatenate([p[1] for p in po]), RTOL, 1e-13)
+
+
+@pytest.mark.parametrize("n", [65, 100, 128, 129, 200, 224])
+def test_sizes_cta_per_object(L, n):
+    rng = np.random.default_rng(200 + n)
+    b = 5
+    xs = [np.sort(rng.uniform(-10, 40, n)) for _ in range(b)]
+    ys = [rng.standard_normal(n) for _ in range(b)]
+    yes = [rng.uniform(0.2, 0.4, n) for _ in range(b)]
+    hyp, nug = [0.7, 1.5], 0.05
+    ll, info, _, _ = run_ll(L, xs, ys, None, yes, hyp, nug)
+    assert not info.any()
+    assert_close(ll, [O.log_likelihood(ys[i], xs[i], hyp, nug, yes[i]) for i in range(b)], RTOL)
+    grid = np.linspace(-12, 42, 37)
+    mean, var, _ = run_predict(L, xs, ys, None, yes, hyp, nug, grid)
+    mo, vo = O.predict(ys[1], xs[1], hyp, nug, grid, yes[1], full_cov=False)
+    assert_close(mean[1], mo, RTOL, 1e-12); assert_close(var[1], vo, RTOL, 1e-12)
+    pred, pvar, pull, resid, _ = run_loo(L, xs, ys, None, yes, hyp, nug)
+    po = O.loo_closed_form(ys[0], xs[0], hyp, nug, yes[0])
+    assert_close(pull[:n], po[2], RTOL, 1e-11)
+
+
+def test_ragged_mixed_sizes_and_empty(L):
+    rng = np.random.default_rng(7)
+    sizes = [60, 0, 3, 64, 17, 1, 40, 0, 59]
+    xs = [np.sort(rng.uniform(0, 30, n)) for n in sizes]
+    ys = [rng.standard_normal(n) for n in sizes]
+    yes = [rng.uniform(0.1, 0.2, n) for n in sizes]
+    hyp, nug = [1.1, 2.5], 0.0
+    ll, info, tot, _ = run_ll(L, xs, ys, None, yes, hyp, nug)
+    assert not info.any()
+    ref = [O.log_likelihood(ys[i], xs[i], hyp, nug, yes[i]) if sizes[i] else 0.0 for i in range(len(sizes))]
+    assert_close(ll, ref, RTOL, 1e-300)
+
+
+def test_not_positive_definite_is_reported(L):
+    """Duplicate epochs with zero noise: scipy.linalg.cholesky raises (inv_matrix.py:23);
+    the C ABI returns the count, a LAPACK-style info and NaN outputs, other objects unaffected."""
+    x_bad = np.array([0.0, 1.0, 1.0, 2.0]); y = np.array([0.1, 0.2, 0.3, 0.4])
+    x_ok = np.array([0.0, 1.0, 1.5, 2.0])
+    ll, info, tot, rc = run_ll(L, [x_ok, x_bad, x_ok], [y, y, y], None, None, [1.0, 1.0], 0.0)
+    assert rc == 1 and info[0] == 0 and info[2] == 0 and info[1] == 3
+    assert np.isnan(ll[1]) and np.isfinite(ll[0]) and np.isnan(tot)
+    with pytest.raises(np.linalg.LinAlgError):
+        O.log_likelihood(y, x_bad, [1.0, 1.0], 0.0)
+
+
+def test_batched_c2_shape_vs_batched_oracle(L):
+    """BASELINE config 2 in miniature (2,000 of the 10^5 light curves x 60 epochs, shared mean)."""
+    rng = np.random.default_rng(2)
+    b, n = 2000, 60
+    x = np.sort(rng.uniform(-10, 40, (b, n)), axis=1)
+    ye = np.full((b, n), 0.2)
+    y0 = -18 + 2 * np.sin(x / 10) + rng.normal(0, 0.3, (b, 1))
+    y = y0 + 0.5 * rng.standard_normal((b, n))
+    hyp, nug = [0.5, 2.0], 0.0
+    ll, info, tot, _ = run_ll(L, list(x), list(y), list(y0), list(ye), hyp, nug)
+    ref = O.ll_batched_1d(x, y, y0, ye, hyp, nug)
+    assert not info.any()
+    assert_close(ll, ref, RTOL); assert_close(tot, ref.sum(), RTOL)
+    grid = np.linspace(-10, 40, 100)
+    mean, var, _ = run_predict(L, list(x), list(y), list(y0), list(ye), hyp, nug, grid, new_y0=np.zeros((b, 100)))
+    mo, vo = O.predict_batched_1d(x, y, y0, ye, hyp, nug, grid, np.zeros((b, 100)))
+    assert_close(mean, mo, RTOL, 1e-12); assert_close(var, vo, RTOL, 1e-13)
