@@ -1,0 +1,189 @@
+"""Device-resident batch of GP objects: the numpy-in / numpy-out layer over the C ABI.
+
+One `DeviceBatch` = the data a reference `Gaussian_process` holds (y, Time, y_err, y0:
+cosmogp/Gaussian_process.py:156-186) packed as CSR arrays and uploaded ONCE to HBM;
+every likelihood evaluation of the optimiser, the prediction and the pulls are then
+single batched launches on it.  PyTorch only owns the buffers (pinned staging + device
+tensors) and the stream; all arithmetic is in libcosmogp_b200.so.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _as_list_of_arrays(seq, dim):
+    out = []
+    for a in seq:
+        a = np.asarray(a, dtype=np.float64)
+        out.append(a.reshape(-1, dim) if dim == 2 else a.reshape(-1))
+    return out
+
+
+def pack_csr(seq, dim=1):
+    """list of per-object arrays (or a 2-D/3-D ndarray of equal-length objects) ->
+    (flat C-contiguous float64 array, offsets int64[B+1])."""
+    if isinstance(seq, np.ndarray) and seq.dtype != object and seq.ndim == (2 if dim == 1 else 3):
+        b, n = seq.shape[0], seq.shape[1]
+        flat = np.ascontiguousarray(seq, dtype=np.float64).reshape(b * n, *([2] if dim == 2 else []))
+        return flat, np.arange(b + 1, dtype=np.int64) * n
+    arrs = _as_list_of_arrays(seq, dim)
+    off = np.zeros(len(arrs) + 1, dtype=np.int64)
+    if arrs:
+        off[1:] = np.cumsum([len(a) for a in arrs])
+        flat = np.ascontiguousarray(np.concatenate(arrs), dtype=np.float64)
+    else:
+        flat = np.zeros((0, 2) if dim == 2 else (0,), dtype=np.float64)
+    return flat, off
+
+
+def pinned_like(a):
+    """Copy a numpy array into pinned host memory (returns the numpy view and its owner)."""
+    t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int64, pin_memory=True)
+    v = t.numpy()
+    v[...] = a
+    return v, t
+
+
+class DeviceBatch:
+    """x: flat (sumN,) or (sumN,2); y, y0, y_err: flat (sumN,) (y0 / y_err may be None);
+    off: int64 (B+1,).  Host arrays may live in pinned memory (fast path) or not."""
+
+    def __init__(self, x, y, off, y0=None, y_err=None, dim=1, device=None, max_n=None):
+        _lib.require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dim = int(dim)
+        self.n_obj = int(len(off) - 1)
+        self.n_pts = int(off[-1]) if len(off) else 0
+        self.off_host = np.ascontiguousarray(off, dtype=np.int64)
+        sizes = np.diff(self.off_host)
+        self.max_n = int(sizes.max()) if max_n is None and self.n_obj else int(max_n or 0)
+        self.h2d_bytes = 0
+        self.off = self._up(self.off_host)
+        self.x = self._up(x)
+        self.y = self._up(y)
+        self.y0 = self._up(y0)
+        self.y_err = self._up(y_err)
+        self._info = torch.empty(max(self.n_obj, 1), dtype=torch.int32, device=self.device)
+        self.d2h_bytes = 0
+
+    # ---- plumbing
+    def _up(self, a):
+        if a is None:
+            return None
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t.to(self.device, non_blocking=True)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def _hyp(self, hyp):
+        h = np.ascontiguousarray(np.asarray(hyp, dtype=np.float64).ravel())
+        need = 2 if self.dim == 1 else 4
+        assert len(h) == need, "expected %d hyperparameters, got %d" % (need, len(h))
+        return h
+
+    def _down(self, t):
+        """Device -> pinned host (torch's caching host allocator recycles the blocks)."""
+        self.d2h_bytes += t.numel() * t.element_size()
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out.numpy()
+
+    # ---- the hot path
+    def ll_dev(self, hyp, nugget=0.0, floor=0.0, flags=0):
+        """Enqueue one batched log-likelihood evaluation; returns (ll_obj, info) device tensors."""
+        h = self._hyp(hyp)
+        ll = torch.empty(max(self.n_obj, 1), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_ll_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                               self._p(self.y), self._p(self.y0), self._p(self.y_err), _lib.hptr(h),
+                                               float(nugget), float(floor), int(flags), self._p(ll), self._p(self._info),
+                                               self._stream())
+        _lib.check(rc, "cgp_ll_batched_dev")
+        return ll[:self.n_obj], self._info[:self.n_obj]
+
+    def log_likelihood(self, hyp, nugget=0.0, floor=0.0, flags=0):
+        """-> (sum over objects in index order, per-object LL, info), all host numpy."""
+        ll, info = self.ll_dev(hyp, nugget, floor, flags)
+        ll_h = self._down(ll)
+        info_h = self._down(info)
+        total = float(np.add.accumulate(ll_h)[-1]) if self.n_obj else 0.0   # left-to-right, like :205-213
+        return total, ll_h, info_h
+
+    def predict_dev(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0):
+        h = self._hyp(hyp)
+        m = 0 if goff is not None else int(grid.shape[0])
+        nout = int(goff[-1].item()) if goff is not None else self.n_obj * m
+        mean = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device)
+        var = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device) if want_var else None
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_predict_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim,
+                                                    self._p(self.x), self._p(self.y), self._p(self.y0),
+                                                    self._p(self.y_err), _lib.hptr(h), float(nugget), float(floor),
+                                                    int(flags), self._p(grid), self._p(goff), m, self._p(new_y0),
+                                                    self._p(mean), self._p(var), self._p(self._info), self._stream())
+        _lib.check(rc, "cgp_predict_batched_dev")
+        return mean[:nout], (var[:nout] if want_var else None), self._info[:self.n_obj]
+
+    def predict(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0):
+        """grid: host array, shared (M,[2]) or per-object flat with goff (int64 B+1).
+        -> mean, var (host; shape (B,M) for a shared grid, flat otherwise), info."""
+        g = self._up(np.asarray(grid, dtype=np.float64))
+        go = self._up(np.asarray(goff, dtype=np.int64)) if goff is not None else None
+        ny0 = self._up(np.asarray(new_y0, dtype=np.float64)) if new_y0 is not None else None
+        mean, var, info = self.predict_dev(hyp, nugget, g, go, ny0, want_var, floor, flags)
+        mean_h = self._down(mean)
+        var_h = self._down(var) if want_var else None
+        info_h = self._down(info)
+        if goff is None:
+            m = int(g.shape[0])
+            mean_h = mean_h.reshape(self.n_obj, m)
+            var_h = var_h.reshape(self.n_obj, m) if want_var else None
+        return mean_h, var_h, info_h
+
+    def loo(self, hyp, nugget, mean=None, mode=_lib.CGP_LOO_PLAIN, floor=0.0, flags=0):
+        """Closed-form leave-one-out; `mean` (flat, host) replaces the batch's y0 when given.
+        -> pred, pred_var, pull, resid (flat host arrays), info."""
+        h = self._hyp(hyp)
+        m = self._up(np.asarray(mean, dtype=np.float64)) if mean is not None else self.y0
+        outs = [torch.empty(max(self.n_pts, 1), dtype=torch.float64, device=self.device) for _ in range(4)]
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_loo_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                                self._p(self.y), self._p(m), self._p(self.y_err), _lib.hptr(h),
+                                                float(nugget), float(floor), int(flags), int(mode),
+                                                *[self._p(o) for o in outs], self._p(self._info), self._stream())
+        _lib.check(rc, "cgp_loo_batched_dev")
+        res = [self._down(o[:self.n_pts]) for o in outs]
+        return res + [self._down(self._info[:self.n_obj])]
+
+    def matrices(self, hyp, nugget, want_k=True, want_kinv=True, floor=0.0, flags=0):
+        """kernel_matrix / inv_kernel_matrix per object (lists of (N,N) host arrays)."""
+        h = self._hyp(hyp)
+        sizes = np.diff(self.off_host)
+        moff_h = np.zeros(self.n_obj + 1, dtype=np.int64)
+        moff_h[1:] = np.cumsum(sizes * sizes)
+        moff = self._up(moff_h)
+        tot = int(moff_h[-1])
+        kmat = torch.empty(max(tot, 1), dtype=torch.float64, device=self.device) if want_k else None
+        kinv = torch.empty(max(tot, 1), dtype=torch.float64, device=self.device) if want_kinv else None
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_matrices_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim,
+                                                     self._p(self.x), self._p(self.y_err), _lib.hptr(h), float(nugget),
+                                                     float(floor), int(flags), self._p(moff), self._p(kmat),
+                                                     self._p(kinv), self._p(self._info), self._stream())
+        _lib.check(rc, "cgp_matrices_batched_dev")
+        out = []
+        for t in (kmat, kinv):
+            if t is None:
+                out.append(None)
+                continue
+            flat = self._down(t[:tot])
+            out.append([flat[moff_h[i]:moff_h[i + 1]].reshape(sizes[i], sizes[i]) for i in range(self.n_obj)])
+        return out[0], out[1], self._down(self._info[:self.n_obj])

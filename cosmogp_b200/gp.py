@@ -1,0 +1,253 @@
+"""Drop-in objects for cosmogp's Gaussian_process / gaussian_process /
+gaussian_process_nobject (cosmogp/Gaussian_process.py:78-393): same constructor
+arguments, methods, attributes and error behaviour; numpy in, numpy out.  The
+per-object Python loops of the reference (:207, :264, :304, :349) are replaced by
+single batched launches on a device-resident copy of the data.
+
+Differences, all supersets:
+  * `svd_method` is accepted everywhere but both values run the device Cholesky path
+    (north_star keeps the SVD only as a host-side reference check, inv_matrix.svd_inverse);
+    a non-positive-definite K therefore raises numpy.linalg.LinAlgError like the
+    reference's svd_method=False path (inv_matrix.py:23) instead of pseudo-inverting.
+  * `get_prediction(COV='diag')` computes only the variance diagonal
+    (`prediction_variance`); COV=True keeps `covariance_matrix`, materialised per object
+    on access.  `kernel_matrix` / `inv_kernel_matrix` are materialised on access too.
+  * `fit_nugget` exists from construction (quirk Q4); `new_binning=None` predicts every
+    object on its own epochs (the reference's stale loop index, quirk Q3, is not kept).
+  * y, Time, y_err may also be 2-D ndarrays (equal-length objects), which avoids
+    10^5 tiny numpy arrays.
+"""
+import numpy as np
+from scipy.optimize import fmin
+
+from . import _lib
+from . import mean as _mean
+from .batch import DeviceBatch, pack_csr
+from .kernel import init_rbf, rbf_kernel_1d, rbf_kernel_2d
+
+
+class _LazyMatrices(object):
+    """list-like of per-object matrices computed on the device on first access."""
+
+    def __init__(self, n, make):
+        self._n, self._make, self._cache = n, make, {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        if i not in self._cache:
+            self._cache[i] = self._make(i)
+        return self._cache[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+
+class Gaussian_process:
+    "Gaussian process regressor (device-backed)."
+
+    def __init__(self, y, Time, kernel='RBF1D',
+                 y_err=None, diff=None, Mean_Y=None,
+                 Time_mean=None, substract_mean=False):
+        kernel_choice = ['RBF1D', 'RBF2D']
+        assert kernel in kernel_choice, '%s is not in implemented kernel' % (kernel)
+
+        self._dim = 1 if kernel == 'RBF1D' else 2
+        self.kernel = rbf_kernel_1d if kernel == 'RBF1D' else rbf_kernel_2d
+        sigma, L = init_rbf(Time, y)                                        # :145-146, :153-154
+        self.hyperparameters = np.array([sigma, L]) if self._dim == 1 else np.array([sigma, L, L, 0.])
+
+        self.y = y
+        self.N_sn = len(y)
+        self.Time = Time
+        self.nugget = 0.
+        self.fit_nugget = False
+        self.flags = 0                      # _lib.CGP_AMP_ON_AUTOCOV to opt out of quirk Q2
+
+        self._x_flat, self._off = pack_csr(Time, self._dim)
+        self._y_flat, off_y = pack_csr(y, 1)
+        assert np.array_equal(self._off, off_y), 'y and Time should have the same structure'
+        if y_err is not None:
+            self.y_err = y_err
+            self._ye_flat, off_e = pack_csr(y_err, 1)
+            assert np.array_equal(self._off, off_e), 'y_err and y should have the same structure'
+        else:
+            self.y_err = [np.zeros(n) for n in np.diff(self._off)]         # :161-169
+            self._ye_flat = None
+
+        self.Mean_Y = Mean_Y
+        self.Time_mean = Time_mean
+        self.substract_mean = substract_mean
+        self.diff = np.array([None] * self.N_sn) if diff is None else diff  # :175-178
+
+        if self.substract_mean or self.Mean_Y is not None:                  # :180-186
+            self._y0_flat, self._diff_used = _mean.batched_mean(
+                self._x_flat, self._y_flat, self._off, self._dim, self.Mean_Y, self.Time_mean, self.diff)
+            self.y0 = [self._y0_flat[self._off[i]:self._off[i + 1]] for i in range(self.N_sn)]
+        else:
+            self._y0_flat, self._diff_used = None, np.zeros(self.N_sn)
+            self.y0 = np.zeros(self.N_sn)
+
+        self.as_the_same_time = True
+        self._batch = None
+
+    # ------------------------------------------------------------------ device state
+    @property
+    def batch(self):
+        if self._batch is None:
+            self._batch = DeviceBatch(self._x_flat, self._y_flat, self._off, y0=self._y0_flat,
+                                      y_err=self._ye_flat, dim=self._dim)
+        return self._batch
+
+    @staticmethod
+    def _raise_if_bad(info):
+        bad = np.nonzero(info)[0]
+        if len(bad):
+            raise np.linalg.LinAlgError(
+                "%d-th leading minor of the covariance of object %d is not positive definite "
+                "(%d object(s) affected)" % (int(info[bad[0]]), int(bad[0]), len(bad)))
+
+    # ------------------------------------------------------------------ likelihood
+    def compute_log_likelihood(self, Hyperparameter, svd_method=True):
+        """Global log likelihood for a set of hyperparameters (:191-213): one launch."""
+        if self.fit_nugget:
+            Nugget = Hyperparameter[-1]
+            hyperparameter = Hyperparameter[:-1]
+        else:
+            Nugget = self.nugget
+            hyperparameter = Hyperparameter
+        total, per_object, info = self.batch.log_likelihood(hyperparameter, Nugget, flags=self.flags)
+        self._raise_if_bad(info)
+        self.log_likelihood_per_object = per_object
+        self.log_likelihood = np.array([total])             # shape (1,), quirk Q5
+
+    def find_hyperparameters(self, hyperparameter_guess=None, nugget=False, svd_method=True):
+        """Maximum likelihood with scipy.optimize.fmin on the host (:216-253); every
+        simplex evaluation is one batched device launch."""
+        if hyperparameter_guess is not None:
+            assert len(self.hyperparameters) == len(hyperparameter_guess), 'should be same len'
+            self.hyperparameters = hyperparameter_guess
+
+        def _compute_log_likelihood(Hyper, svd_method=svd_method):
+            self.compute_log_likelihood(Hyper, svd_method=svd_method)
+            return -self.log_likelihood[0]
+
+        initial_guess = [self.hyperparameters[i] for i in range(len(self.hyperparameters))]
+        if nugget:
+            self.fit_nugget = True
+            initial_guess.append(1.)
+        else:
+            self.fit_nugget = False
+
+        hyperparameters = fmin(_compute_log_likelihood, initial_guess, disp=False)
+
+        for i in range(len(self.hyperparameters)):
+            self.hyperparameters[i] = np.sqrt(hyperparameters[i] ** 2)
+        if self.fit_nugget:
+            self.nugget = np.sqrt(hyperparameters[-1] ** 2)
+
+    # ------------------------------------------------------------------ matrices
+    def compute_kernel_matrix(self):
+        """kernel_matrix[sn] = K(Time[sn]) with nugget and y_err (:256-267), on access."""
+        hyp, nug = np.array(self.hyperparameters, dtype=float), float(self.nugget)
+        self.kernel_matrix = _LazyMatrices(self.N_sn, lambda i: self._object_matrices(i, hyp, nug)[0])
+
+    def _object_matrices(self, i, hyp, nug):
+        o0, o1 = self._off[i], self._off[i + 1]
+        sub = DeviceBatch(self._x_flat[o0:o1], self._y_flat[o0:o1], np.array([0, o1 - o0], dtype=np.int64),
+                          y_err=None if self._ye_flat is None else self._ye_flat[o0:o1], dim=self._dim)
+        if sub.max_n > _lib.CGP_SMALL_MAX_N:
+            from . import dense
+            return dense.object_matrices(sub, hyp, nug, self.flags)
+        k, kinv, info = sub.matrices(hyp, nug, flags=self.flags)
+        self._raise_if_bad(info)
+        return k[0], kinv[0]
+
+    # ------------------------------------------------------------------ prediction
+    def get_prediction(self, new_binning=None, COV=True, svd_method=True):
+        """Interpolation (and its covariance) on a new grid (:270-361).
+
+        new_binning None -> each object's own epochs.  COV: True (full matrices on
+        access + diagonal), 'diag' (diagonal only) or False."""
+        hyp, nug = np.array(self.hyperparameters, dtype=float), float(self.nugget)
+        has_mean = self.substract_mean or self.Mean_Y is not None
+        self.compute_kernel_matrix()
+        self.inv_kernel_matrix = _LazyMatrices(self.N_sn, lambda i: self._object_matrices(i, hyp, nug)[1])
+        want_var = bool(COV)
+
+        if new_binning is None:
+            self.as_the_same_time = True
+            self.new_binning = self.Time
+            grid, goff = self._x_flat, self._off
+            new_y0 = self._y0_flat if has_mean else None                   # :308-309
+            mean, var, info = self.batch.predict(hyp, nug, grid, goff=goff, new_y0=new_y0,
+                                                 want_var=want_var, flags=self.flags)
+            self._raise_if_bad(info)
+            self.Prediction = [mean[goff[i]:goff[i + 1]] for i in range(self.N_sn)]
+            self.prediction_variance = [var[goff[i]:goff[i + 1]] for i in range(self.N_sn)] if want_var else None
+        else:
+            self.as_the_same_time = False
+            self.new_binning = new_binning
+            grid = np.ascontiguousarray(new_binning, dtype=np.float64)
+            m = len(grid)
+            new_y0 = None
+            if has_mean:                                                    # :310-312 via mean.py:92-101
+                tmpl = _mean.template_on_grid(grid, self._dim, self.Mean_Y, self.Time_mean)
+                if tmpl is not None:
+                    new_y0 = tmpl[None, :] + self._diff_used[:, None]
+                else:
+                    # no template: return_mean hands back y0 (per-epoch constant = diff) for any new_x;
+                    # it only broadcasts in the reference when it is a scalar per object
+                    new_y0 = np.repeat(self._diff_used[:, None], m, axis=1)
+            mean, var, info = self.batch.predict(hyp, nug, grid, new_y0=new_y0, want_var=want_var, flags=self.flags)
+            self._raise_if_bad(info)
+            self.Prediction = list(mean)
+            self.prediction_variance = list(var) if want_var else None
+        self.warning_pf = new_y0
+        if COV is True:
+            self.get_covariance_matrix()
+
+    def get_covariance_matrix(self):
+        """covariance_matrix[sn] = K(grid,grid)+nugget^2 - H K^-1 H^T (:340-361), on access."""
+        from . import dense
+        hyp, nug = np.array(self.hyperparameters, dtype=float), float(self.nugget)
+
+        def make(i):
+            o0, o1 = self._off[i], self._off[i + 1]
+            grid = self._x_flat[o0:o1] if self.as_the_same_time else np.ascontiguousarray(self.new_binning, dtype=np.float64)
+            return dense.predictive_covariance(
+                self._x_flat[o0:o1], None if self._ye_flat is None else self._ye_flat[o0:o1],
+                grid, hyp, nug, self._dim, self.flags)
+
+        self.covariance_matrix = _LazyMatrices(self.N_sn, make)
+
+
+class gaussian_process(Gaussian_process):
+
+    def __init__(self, y, Time, kernel='RBF1D',
+                 y_err=None, diff=None, Mean_Y=None,
+                 Time_mean=None, substract_mean=False):
+        """Run gp for one object (:365-379): y, Time, y_err are wrapped in 1-lists, diff is not (Q14)."""
+        if y_err is not None:
+            y_err = [y_err]
+        Gaussian_process.__init__(self, [y], [Time], kernel=kernel,
+                                  y_err=y_err, Mean_Y=Mean_Y, Time_mean=Time_mean,
+                                  diff=diff, substract_mean=substract_mean)
+
+
+class gaussian_process_nobject(Gaussian_process):
+
+    def __init__(self, y, Time, kernel='RBF1D',
+                 y_err=None, diff=None, Mean_Y=None,
+                 Time_mean=None, substract_mean=False):
+        """Run gp for n objects (:382-393)."""
+        Gaussian_process.__init__(self, y, Time, kernel=kernel,
+                                  y_err=y_err, diff=diff, Mean_Y=Mean_Y,
+                                  Time_mean=Time_mean, substract_mean=substract_mean)
