@@ -36,11 +36,11 @@ static int make_cov(int dim, const double* hyp, double nugget, double floor, uns
   const double s2 = hyp[0] * hyp[0];
   if (dim == 1) {
     c->amp_auto = s2; c->amp_cross = s2;
-    c->m00 = 1.0 / (hyp[1] * hyp[1]); c->m01x2 = 0.0; c->m11 = 0.0;
+    c->h00 = -0.5 / (hyp[1] * hyp[1]); c->h01 = 0.0; c->h11 = 0.0;
   } else if (dim == 2) {
     const double lx2 = hyp[1] * hyp[1], ly2 = hyp[2] * hyp[2], lxy = hyp[3];
     const double sc = 1.0 / (lx2 * ly2 - lxy * lxy);        // NaN/inf metric propagates, like scipy
-    c->m00 = ly2 * sc; c->m01x2 = 2.0 * (-lxy * sc); c->m11 = lx2 * sc;
+    c->h00 = -0.5 * (ly2 * sc); c->h01 = lxy * sc; c->h11 = -0.5 * (lx2 * sc);
     c->amp_cross = s2;
     c->amp_auto = (flags & CGP_AMP_ON_AUTOCOV) ? s2 : 1.0;  // HEAD drops sigma^2 (kernel.py:146-148)
   } else {

@@ -6,12 +6,13 @@
 namespace cgp {
 
 // Covariance function, prepared on the host from hyp / nugget / floor / flags.
-//   K(a,b) = amp * exp(-q/2);  1D: q = (a-b)^2 * m00 (m00 = 1/l^2, cosmogp/kernel.py:71-72)
-//   2D: q = dx^2 m00 + dx dy m01x2 + dy^2 m11 (inverse metric, cosmogp/kernel.py:127-130)
+//   K(a,b) = amp * exp(-q/2);  1D: q = (a-b)^2 / l^2 (cosmogp/kernel.py:71-72)
+//   2D: q = d^T M d with M the inverse metric (cosmogp/kernel.py:127-130).
+//   h00, h01, h11 hold -M00/2, -M01, -M11/2, so that -q/2 = dx^2 h00 + dx dy h01 + dy^2 h11.
 struct Cov {
   double amp_auto;     // auto-covariance amplitude: sigma^2 (1D) or 1 (2D at HEAD, kernel.py:146-148)
   double amp_cross;    // cross-covariance amplitude: sigma^2 (kernel.py:72,141)
-  double m00, m01x2, m11;
+  double h00, h01, h11;
   double noise_const;  // floor^2 + nugget^2, added to y_err^2 on the diagonal (kernel.py:75,151)
   double nugget2;      // nugget^2: K(x*,x*) carries it but not y_err^2 (Gaussian_process.py:357)
 };

@@ -20,6 +20,7 @@
 // data movement, all three products the algorithm needs:
 //   X*Y^T (frag, frag)   X*Y (frag, fragT)   X^T*Y (fragT, fragT).
 #include "cgp_internal.h"
+#include "cgp_math.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -75,18 +76,15 @@ template <int WARPS> __device__ __forceinline__ void cta_sync() {
   if (WARPS == 1) __syncwarp(); else __syncthreads();
 }
 
-// q/2 exponent of the RBF: 1D (a-b)^2/l^2, 2D Mahalanobis form under the inverse metric.
+// RBF exponent -q/2 (<= 0): 1D -(a-b)^2/(2 l^2); 2D Mahalanobis form under the inverse
+// metric.  Cov carries the metric pre-multiplied by -1/2, so this is 3 (1D) / 7 (2D) FP64 ops.
 template <int DIM>
-__device__ __forceinline__ double rbf(const Cov& c, double amp, double ax, double ay, double bx, double by) {
-  double dx = ax - bx;
-  double q;
-  if (DIM == 1) {
-    q = dx * dx * c.m00;
-  } else {
-    double dy = ay - by;
-    q = dx * dx * c.m00 + dx * dy * c.m01x2 + dy * dy * c.m11;
-  }
-  return amp * exp(-0.5 * q);
+__device__ __forceinline__ double rbf_arg(const Cov& c, double ax, double ay, double bx, double by) {
+  const double dx = ax - bx;
+  if (DIM == 1) return dx * dx * c.h00;
+  const double dy = ay - by;
+  const double u = fma(dx, c.h00, dy * c.h01);
+  return fma(dy * c.h11, dy, u * dx);
 }
 
 // In-register Cholesky of one 8x8 diagonal tile held in accumulator layout (lower
@@ -104,7 +102,7 @@ __device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
     const double ak = (k & 1) ? a1 : a0;                            // A[g][k] on lanes with t == kc
     const double d = __shfl_sync(FULL, ak, k * 4 + kc);             // pivot
     if (!(d > 0.0) && badk == 0) badk = k + 1;
-    const double rinv = rsqrt(d);
+    const double rinv = cgp_rsqrt(d);
     pivprod *= d;
     const double lg = __shfl_sync(FULL, ak, L.g * 4 + kc) * rinv;            // L[g][k]
     const double lc0 = __shfl_sync(FULL, ak, (2 * L.t) * 4 + kc) * rinv;     // L[2t][k]
@@ -122,6 +120,29 @@ template <int TASK> __host__ __device__ constexpr int n_vec() {
 }
 
 // ---------------------------------------------------------------------------------------
+// Covariance entry e = exp(-q/2) between staged points i and j (amplitude applied by the caller).
+template <int DIM>
+__device__ __forceinline__ double cov_e(const Cov& c, const double* px, int ld, int i, int j) {
+  return cgp_exp(rbf_arg<DIM>(c, px[i], DIM == 2 ? px[ld + i] : 0.0, px[j], DIM == 2 ? px[ld + j] : 0.0));
+}
+
+// K tile (I,J) minus the accumulated update s, in accumulator layout.  Rows/cols >= n pad
+// with the identity; the strict upper triangle of a diagonal tile is never read.
+template <int DIM>
+__device__ __forceinline__ void k_tile_minus(const Cov& cov, const double* px, const double* noise, int ld, int n,
+                                             int I, int J, const Lane& L, double s0, double s1,
+                                             double& k0, double& k1) {
+  const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
+  double e0 = 0.0, e1 = 0.0;
+  if (gi < n && cj < gi) e0 = cov_e<DIM>(cov, px, ld, gi, cj);
+  if (gi < n && cj + 1 < gi) e1 = cov_e<DIM>(cov, px, ld, gi, cj + 1);
+  k0 = fma(cov.amp_auto, e0, -s0);
+  k1 = fma(cov.amp_auto, e1, -s1);
+  const double dg = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
+  if (cj == gi) k0 = dg - s0;
+  if (cj + 1 == gi) k1 = dg - s1;
+}
+
 template <int DIM, int TASK, int NB_MAX, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 small_gp_kernel(const SmallArgs a, const int nbm) {
@@ -142,7 +163,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
   double* vd = va + ld;                                   // diag(K^-1)
   double* v1 = vd + ld;                                   // L^-1 1
   double* vu = v1 + ld;                                   // K^-1 1
-  __shared__ double s_scal[4];                            // logdet, quad, sum r
+  __shared__ double s_rsum;
   __shared__ int s_bad;
 
   const int split = (TASK == TASK_PREDICT) ? a.split : 1;
@@ -174,53 +195,69 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
         vr[i] = r; rsum += r;
       }
     }
-    if (tid == 0) { s_scal[0] = 0.0; s_scal[1] = 0.0; s_scal[2] = 0.0; s_bad = 0; }
+    if (tid == 0) { s_rsum = 0.0; s_bad = 0; }
     cta_sync<WARPS>();
     if (TASK == TASK_LOO && a.loo_mode == 1) {
       rsum = red_warp(rsum);
-      if (lane == 0) atomicAdd(&s_scal[2], rsum);
+      if (lane == 0) atomicAdd(&s_rsum, rsum);
     }
 
-    // ---------------- left-looking block Cholesky; slot(J,J) receives T_J = L_JJ^-1
+    // ---------------- left-looking block Cholesky; slot(J,J) receives T_J = L_JJ^-1.
+    // log det accumulates as mantissa * 2^exponent of the pivot product (one log per object).
+    double lp_m = 1.0; int lp_e = 0;
     for (int J = 0; J < nb; ++J) {
-      for (int I = J + warp; I < nb; I += WARPS) {
-        double s0 = 0.0, s1 = 0.0;
+      // tiles of block column J owned by this warp, two at a time; each tile accumulates its
+      // rank-8J update on two independent DMMA chains (k-halves) -> 4 chains in flight
+      for (int I = J + warp; I < nb; I += 2 * WARPS) {
+        const int I2 = I + WARPS;
+        const bool two = I2 < nb;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        const double* tj = tiles + slot(J, 0) * TILE + L.fr;
+        const double* ti = tiles + slot(I, 0) * TILE + L.fr;
+        const double* ti2 = tiles + slot(two ? I2 : I, 0) * TILE + L.fr;
+#pragma unroll 2
         for (int P = 0; P < J; ++P) {
-          const double2 fa = ld_frag(tiles, slot(I, P), L);
-          const double2 fb = ld_frag(tiles, slot(J, P), L);
-          dmma(s0, s1, fa.x, fb.x); dmma(s0, s1, fa.y, fb.y);
+          const double2 fb = *reinterpret_cast<const double2*>(tj + P * TILE);
+          const double2 fa = *reinterpret_cast<const double2*>(ti + P * TILE);
+          const double2 fc = *reinterpret_cast<const double2*>(ti2 + P * TILE);
+          dmma(a0, a1, fa.x, fb.x); dmma(b0, b1, fa.y, fb.y);
+          dmma(c0, c1, fc.x, fb.x); dmma(d0, d1, fc.y, fb.y);
         }
-        // K tile (I,J) in accumulator layout; rows/cols >= n pad with the identity
-        const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
-        double k0 = 0.0, k1 = 0.0;
-        {
-          const double xi = px[gi], yi = (DIM == 2) ? px[ld + gi] : 0.0;
-          if (gi < n && cj < gi) k0 = rbf<DIM>(cov, cov.amp_auto, xi, yi, px[cj], (DIM == 2) ? px[ld + cj] : 0.0);
-          if (gi < n && cj + 1 < gi) k1 = rbf<DIM>(cov, cov.amp_auto, xi, yi, px[cj + 1], (DIM == 2) ? px[ld + cj + 1] : 0.0);
-          if (cj == gi) k0 = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
-          if (cj + 1 == gi) k1 = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
-        }
-        k0 -= s0; k1 -= s1;
+        double k0, k1;
+        k_tile_minus<DIM>(cov, px, noise, ld, n, I, J, L, a0 + b0, a1 + b1, k0, k1);
         if (I == J) {                                     // warp 0
           double t0, t1, piv; int badk;
           diag_factor(k0, k1, L, t0, t1, piv, badk);
           st_acc(tiles, slot(J, J), L, t0, t1);
-          if (lane == 0) {
-            s_scal[0] += log(piv);
-            if (badk && s_bad == 0) s_bad = 8 * J + badk;
+          if (TASK == TASK_LL) {
+            lp_m *= piv;
+            const int hi = __double2hiint(lp_m);
+            const int e = ((hi >> 20) & 0x7ff) - 1023;
+            lp_e += e;
+            lp_m = __hiloint2double(hi - (e << 20), __double2loint(lp_m));
           }
+          if (badk && lane == 0 && s_bad == 0) s_bad = 8 * J + badk;
         } else {
           st_acc(tiles, slot(I, J), L, k0, k1);           // park C[I][J] in its own slot
+        }
+        if (two) {
+          k_tile_minus<DIM>(cov, px, noise, ld, n, I2, J, L, c0 + d0, c1 + d1, k0, k1);
+          st_acc(tiles, slot(I2, J), L, k0, k1);
         }
       }
       cta_sync<WARPS>();
       const double2 ft = ld_frag(tiles, slot(J, J), L);
-      for (int I = J + 1 + warp; I < nb; I += WARPS) {    // L[I][J] = C[I][J] T_J^T
+      for (int I = J + 1 + warp; I < nb; I += 2 * WARPS) {    // L[I][J] = C[I][J] T_J^T
+        const int I2 = I + WARPS;
+        const bool two = I2 < nb;
         const double2 fc = ld_frag(tiles, slot(I, J), L);
-        double d0 = 0.0, d1 = 0.0;
-        dmma(d0, d1, fc.x, ft.x); dmma(d0, d1, fc.y, ft.y);
+        const double2 fe = ld_frag(tiles, slot(two ? I2 : I, J), L);
+        double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
+        dmma(d0, d1, fc.x, ft.x); dmma(e0, e1, fc.y, ft.y);
+        dmma(f0, f1, fe.x, ft.x); dmma(g0, g1, fe.y, ft.y);
         __syncwarp();
-        st_acc(tiles, slot(I, J), L, d0, d1);
+        st_acc(tiles, slot(I, J), L, d0 + e0, d1 + e1);
+        if (two) st_acc(tiles, slot(I2, J), L, f0 + g0, f1 + g1);
       }
       cta_sync<WARPS>();
     }
@@ -230,13 +267,14 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
       if (warp == 0) {
         double quad = 0.0;
         for (int J = 0; J < nb; ++J) {
-          double p = 0.0;
+          double p = 0.0, p2 = 0.0;
+          const double* tj = tiles + slot(J, 0) * TILE + L.fr;
           for (int P = 0; P < J; ++P) {
-            const double2 f = ld_frag(tiles, slot(J, P), L);
-            p = fma(f.x, vr[8 * P + L.t], p); p = fma(f.y, vr[8 * P + 4 + L.t], p);
+            const double2 f = *reinterpret_cast<const double2*>(tj + P * TILE);
+            p = fma(f.x, vr[8 * P + L.t], p); p2 = fma(f.y, vr[8 * P + 4 + L.t], p2);
           }
-          const double wv = vr[8 * J + L.g] - red_t(p);
-          const double2 f = ld_frag(tiles, slot(J, J), L);
+          const double wv = vr[8 * J + L.g] - red_t(p + p2);
+          const double2 f = *reinterpret_cast<const double2*>(tj + J * TILE);
           double q = f.x * __shfl_sync(FULL, wv, L.t * 4) + f.y * __shfl_sync(FULL, wv, (4 + L.t) * 4);
           q = red_t(q);
           if (L.t == 0) { vr[8 * J + L.g] = q; quad = fma(q, q, quad); }
@@ -246,25 +284,29 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
         if (lane == 0) {
           const int bad = s_bad;
           a.info[b] = bad;
-          a.ll[b] = bad ? nan("") : -0.5 * (quad + s_scal[0] + n * LOG_2PI);
+          const double logdet = log(lp_m) + (double)lp_e * 0.693147180559945309417232;
+          a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
         }
       }
       continue;
     }
 
     // ---------------- L^-1, row by row, in place (slot(I,J) <- L^-1[I][J]);
-    // L^-1[I][J] = -T_I * sum_{P=J..I-1} L[I][P] L^-1[P][J]
+    // L^-1[I][J] = -T_I * sum_{P=J..I-1} L[I][P] L^-1[P][J]; one A fragment per P feeds all J <= P
     for (int I = 1; I < nb; ++I) {
       double s0[KMAX], s1[KMAX];
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        const int J = warp + k * WARPS;
-        s0[k] = 0.0; s1[k] = 0.0;
-        if (J < I) {
-          for (int P = J; P < I; ++P) {
-            const double2 fa = ld_frag(tiles, slot(I, P), L);
-            const double2 fb = ld_fragT(tiles, slot(P, J), L);
-            dmma(s0[k], s1[k], fa.x, fb.x); dmma(s0[k], s1[k], fa.y, fb.y);
+      for (int k = 0; k < KMAX; ++k) { s0[k] = 0.0; s1[k] = 0.0; }
+      const double* ti = tiles + slot(I, 0) * TILE + L.fr;
+      for (int P = 0; P < I; ++P) {
+        const double2 fa = *reinterpret_cast<const double2*>(ti + P * TILE);
+        const double* tp = tiles + slot(P, 0) * TILE;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int J = warp + k * WARPS;
+          if (J <= P) {
+            const double* q = tp + J * TILE;
+            dmma(s0[k], s1[k], fa.x, q[L.tr0]); dmma(s0[k], s1[k], fa.y, q[L.tr1]);
           }
         }
       }
@@ -277,10 +319,10 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
           st_acc(tiles, slot(I, J), L, s0[k], s1[k]);
           __syncwarp();
           const double2 fs = ld_fragT(tiles, slot(I, J), L);
-          double d0 = 0.0, d1 = 0.0;
-          dmma(d0, d1, ft.x, fs.x); dmma(d0, d1, ft.y, fs.y);
+          double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+          dmma(d0, d1, ft.x, fs.x); dmma(e0, e1, ft.y, fs.y);
           __syncwarp();
-          st_acc(tiles, slot(I, J), L, -d0, -d1);
+          st_acc(tiles, slot(I, J), L, -(d0 + e0), -(d1 + e1));
         }
       }
       cta_sync<WARPS>();
@@ -293,10 +335,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
       if (a.kmat) {
         for (int e = tid; e < n * n; e += NT) {
           const int i = e / n, j = e - i * n;
-          double v;
-          if (i == j) v = cov.amp_auto + noise[i];
-          else v = rbf<DIM>(cov, cov.amp_auto, px[i], (DIM == 2) ? px[ld + i] : 0.0, px[j], (DIM == 2) ? px[ld + j] : 0.0);
-          a.kmat[mo + e] = v;
+          a.kmat[mo + e] = (i == j) ? cov.amp_auto + noise[i] : cov.amp_auto * cov_e<DIM>(cov, px, ld, i, j);
         }
       }
       if (a.kinv) {       // K^-1 = L^-T L^-1: tile (I,J) = sum_{P>=I} Linv[P][I]^T Linv[P][J]
@@ -324,15 +363,16 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
     // ---------------- z = L^-1 r  (and L^-1 1), then alpha = L^-T z, d = colnorm^2(L^-1), u = L^-T(L^-1 1)
     const bool want_u = (TASK == TASK_LOO) && (a.loo_mode == 1);
     for (int I = warp; I < nb; I += WARPS) {
-      double p = 0.0, p1 = 0.0;
+      double p = 0.0, p2 = 0.0, p1 = 0.0;
+      const double* ti = tiles + slot(I, 0) * TILE + L.fr;
       for (int J = 0; J <= I; ++J) {
-        const double2 f = ld_frag(tiles, slot(I, J), L);
-        p = fma(f.x, vr[8 * J + L.t], p); p = fma(f.y, vr[8 * J + 4 + L.t], p);
+        const double2 f = *reinterpret_cast<const double2*>(ti + J * TILE);
+        p = fma(f.x, vr[8 * J + L.t], p); p2 = fma(f.y, vr[8 * J + 4 + L.t], p2);
         if (want_u) {                                     // padded columns multiply exact zeros of L^-1
           p1 += f.x; p1 += f.y;
         }
       }
-      p = red_t(p);
+      p = red_t(p + p2);
       if (L.t == 0) vz[8 * I + L.g] = p;
       if (want_u) { p1 = red_t(p1); if (L.t == 0) v1[8 * I + L.g] = (8 * I + L.g < n) ? p1 : 0.0; }
     }
@@ -369,7 +409,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
       // ---------------- closed-form leave-one-out (pull.py:66-94)
       const double rho = cov.amp_cross / cov.amp_auto;
       const double amp_star = cov.amp_auto + cov.nugget2;
-      const double rs = s_scal[2];
+      const double rs = s_rsum;
       for (int i = tid; i < n; i += NT) {
         const double d = vd[i], r = vr[i];
         const double yv = a.y[o0 + i];
@@ -393,7 +433,8 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
     }
 
     if (TASK == TASK_PREDICT) {
-      // ---------------- grid points in blocks of 8: v = L^-1 h, mean = h.alpha + y0*, var = amp* - |v|^2
+      // ---------------- grid points in blocks of 8: v = L^-1 h, mean = h.alpha + y0*, var = amp* - |v|^2.
+      // h is kept WITHOUT its amplitude (applied once per grid point at the end).
       const int64_t g0 = a.goff ? a.goff[b] : 0;
       const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
       const int64_t out0 = a.goff ? g0 : b * a.m_shared;
@@ -410,31 +451,29 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
         double acc0[NB_MAX], acc1[NB_MAX];
 #pragma unroll
         for (int J = 0; J < NB_MAX; ++J) { acc0[J] = 0.0; acc1[J] = 0.0; }
-        double pm = 0.0;
+        double pm = 0.0, pm2 = 0.0;
+#pragma unroll 1
+        for (int P = 0; P < nb; ++P) {
+          const int c0 = 8 * P + L.t, c1 = c0 + 4;
+          double h0 = 0.0, h1 = 0.0;                      // A fragment of the cross-covariance block
+          if (live && c0 < n) h0 = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c0], DIM == 2 ? px[ld + c0] : 0.0));
+          if (live && c1 < n) h1 = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c1], DIM == 2 ? px[ld + c1] : 0.0));
+          pm = fma(h0, va[c0], pm); pm2 = fma(h1, va[c1], pm2);
 #pragma unroll
-        for (int P = 0; P < NB_MAX; ++P) {
-          if (P < nb) {
-            const int c0 = 8 * P + L.t, c1 = c0 + 4;
-            double h0 = 0.0, h1 = 0.0;                    // A fragment of the cross-covariance block
-            if (live && c0 < n) h0 = rbf<DIM>(cov, cov.amp_cross, gx, gy, px[c0], (DIM == 2) ? px[ld + c0] : 0.0);
-            if (live && c1 < n) h1 = rbf<DIM>(cov, cov.amp_cross, gx, gy, px[c1], (DIM == 2) ? px[ld + c1] : 0.0);
-            pm = fma(h0, va[c0], pm); pm = fma(h1, va[c1], pm);
-#pragma unroll
-            for (int J = P; J < NB_MAX; ++J) {
-              if (J < nb) {
-                const double2 fb = ld_frag(tiles, slot(J, P), L);
-                dmma(acc0[J], acc1[J], h0, fb.x); dmma(acc0[J], acc1[J], h1, fb.y);
-              }
+          for (int J = 0; J < NB_MAX; ++J) {
+            if (J >= P && J < nb) {
+              const double2 fb = ld_frag(tiles, slot(J, P), L);
+              dmma(acc0[J], acc1[J], h0, fb.x); dmma(acc0[J], acc1[J], h1, fb.y);
             }
           }
         }
-        double vv = 0.0;
+        double vv = 0.0, vv2 = 0.0;
 #pragma unroll
-        for (int J = 0; J < NB_MAX; ++J) { vv = fma(acc0[J], acc0[J], vv); vv = fma(acc1[J], acc1[J], vv); }
-        pm = red_t(pm); vv = red_t(vv);
+        for (int J = 0; J < NB_MAX; ++J) { vv = fma(acc0[J], acc0[J], vv); vv2 = fma(acc1[J], acc1[J], vv2); }
+        pm = red_t(pm + pm2); vv = red_t(vv + vv2);
         if (live && L.t == 0) {
-          double mean = pm + (a.new_y0 ? a.new_y0[out0 + mi] : 0.0);
-          double var = amp_star - vv;
+          double mean = fma(cov.amp_cross, pm, a.new_y0 ? a.new_y0[out0 + mi] : 0.0);
+          double var = fma(-cov.amp_cross * cov.amp_cross, vv, amp_star);
           if (bad) { mean = nan(""); var = mean; }
           a.mean[out0 + mi] = mean;
           if (a.var) a.var[out0 + mi] = var;
