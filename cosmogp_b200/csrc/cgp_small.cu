@@ -24,6 +24,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace cgp {
 namespace {
@@ -452,18 +453,20 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
 #pragma unroll
         for (int J = 0; J < NB_MAX; ++J) { acc0[J] = 0.0; acc1[J] = 0.0; }
         double pm = 0.0, pm2 = 0.0;
-#pragma unroll 1
-        for (int P = 0; P < nb; ++P) {
-          const int c0 = 8 * P + L.t, c1 = c0 + 4;
-          double h0 = 0.0, h1 = 0.0;                      // A fragment of the cross-covariance block
-          if (live && c0 < n) h0 = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c0], DIM == 2 ? px[ld + c0] : 0.0));
-          if (live && c1 < n) h1 = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c1], DIM == 2 ? px[ld + c1] : 0.0));
-          pm = fma(h0, va[c0], pm); pm2 = fma(h1, va[c1], pm2);
 #pragma unroll
-          for (int J = 0; J < NB_MAX; ++J) {
-            if (J >= P && J < nb) {
-              const double2 fb = ld_frag(tiles, slot(J, P), L);
-              dmma(acc0[J], acc1[J], h0, fb.x); dmma(acc0[J], acc1[J], h1, fb.y);
+        for (int P = 0; P < NB_MAX; ++P) {
+          if (P < nb) {
+            const int c0 = 8 * P + L.t, c1 = c0 + 4;
+            double h0 = 0.0, h1 = 0.0;                    // A fragment of the cross-covariance block
+            if (live && c0 < n) h0 = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c0], DIM == 2 ? px[ld + c0] : 0.0));
+            if (live && c1 < n) h1 = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c1], DIM == 2 ? px[ld + c1] : 0.0));
+            pm = fma(h0, va[c0], pm); pm2 = fma(h1, va[c1], pm2);
+#pragma unroll
+            for (int J = P; J < NB_MAX; ++J) {            // compile-time triangle: no wasted DMMA
+              if (J < nb) {
+                const double2 fb = ld_frag(tiles, slot(J, P), L);
+                dmma(acc0[J], acc1[J], h0, fb.x); dmma(acc0[J], acc1[J], h1, fb.y);
+              }
             }
           }
         }
@@ -508,9 +511,22 @@ int launch_one(int nbm, const SmallArgs& a, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
+// warps per object for nb <= 8: tuned per task on B200 (override: CGP_SMALL_WARPS=1|2|4)
+static int small_warps(int task) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("CGP_SMALL_WARPS"); forced = e ? atoi(e) : 0; }
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  return task == TASK_PREDICT ? 4 : 1;     // B200, C2 shape: predict 9.2 / 8.3 / 7.7 ms at 1 / 2 / 4 warps; LL 2.1 / 2.6 / 3.2
+}
+
 template <int DIM, int TASK>
 int launch_cfg(int nbm, const SmallArgs& a, cudaStream_t stream) {
-  if (nbm <= 8) return launch_one<DIM, TASK, 8, 1>(nbm, a, stream);
+  if (nbm <= 8) {
+    const int w = small_warps(TASK);
+    if (w == 2) return launch_one<DIM, TASK, 8, 2>(nbm, a, stream);
+    if (w == 4) return launch_one<DIM, TASK, 8, 4>(nbm, a, stream);
+    return launch_one<DIM, TASK, 8, 1>(nbm, a, stream);
+  }
   if (nbm <= 16) return launch_one<DIM, TASK, 16, 4>(nbm, a, stream);
   return launch_one<DIM, TASK, 28, 4>(nbm, a, stream);
 }
