@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 #include <vector>
 
 namespace cgp {
@@ -314,6 +315,96 @@ int cgp_matrices_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int d
   a.n_obj = n_obj; a.off = off; a.x = x; a.yerr = y_err; a.info = info;
   a.moff = moff; a.kmat = kmat; a.kinv = kinv;
   return run_small(TASK_MATRICES, dim, max_n, a, st, "cgp_matrices_batched_dev");
+}
+
+
+// ==================================================================================== large objects
+int64_t cgp_pad128(int64_t n) { return n <= 0 ? 128 : (n + 127) / 128 * 128; }
+
+int cgp_cov_matrix_dev(int dim, const double* x, int64_t n, const double* xnew, int64_t m,
+                       const double* y_err, const double* hyp, double nugget, double floor, unsigned flags,
+                       double* out, int64_t ld, int64_t rows_pad, int64_t cols_pad, void* stream) {
+  if (!x || !out || n < 0 || ld < cols_pad || cols_pad < n) return fail(CGP_ERR_ARG, "cgp_cov_matrix_dev: bad arguments");
+  if (ld % 2 || ((uintptr_t)out & 15)) return fail(CGP_ERR_ARG, "cgp_cov_matrix_dev: out must be 16-byte aligned with even ld");
+  Cov c; int rc = make_cov(dim, hyp, nugget, floor, flags, &c);
+  if (rc) return rc;
+  const int autocov = xnew == nullptr;
+  if (autocov && rows_pad > 65535) {
+    // slabs of rows: the builder's diagonal test is slab-relative, so build >65535-row
+    // auto-covariances as cross blocks plus a diagonal pass is not needed below 65535 stars
+    return fail(CGP_ERR_SIZE, "cgp_cov_matrix_dev: auto-covariance limited to 65535 rows");
+  }
+  int e = large_cov_build(dim, c, autocov, x, n, autocov ? x : xnew, autocov ? n : m, y_err, out, ld, rows_pad, cols_pad,
+                          (cudaStream_t)stream);
+  return e ? cuda_fail(e, "cgp_cov_matrix_dev") : 0;
+}
+
+int cgp_potrf_dev(double* a, int64_t n_pad, int64_t ld, double* logdet, int* info, void* stream) {
+  if (!a || n_pad <= 0 || n_pad % 128 || ld < n_pad || ld % 2) return fail(CGP_ERR_ARG, "cgp_potrf_dev: n_pad must be a positive multiple of 128, ld even");
+  int e = large_potrf(a, n_pad, ld, logdet, info, (cudaStream_t)stream);
+  return e ? cuda_fail(e, "cgp_potrf_dev") : 0;
+}
+
+int cgp_potrs_dev(const double* a, int64_t n_pad, int64_t ld, double* v, double* z_out, int backward, void* stream) {
+  if (!a || !v || n_pad <= 0 || n_pad % 128) return fail(CGP_ERR_ARG, "cgp_potrs_dev: bad arguments");
+  int e = large_potrs(a, n_pad, ld, v, z_out, backward, (cudaStream_t)stream);
+  return e ? cuda_fail(e, "cgp_potrs_dev") : 0;
+}
+
+int cgp_large_solve_dev(const double* a, int64_t n, int64_t n_pad, int64_t ld,
+                        const double* y, const double* y0, double* alpha, double* quad, void* stream) {
+  if (!a || !y || !alpha || n <= 0 || n_pad < n || n_pad % 128) return fail(CGP_ERR_ARG, "cgp_large_solve_dev: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int e = large_residual(y, y0, n, n_pad, alpha, st);
+  if (!e) e = large_potrs(a, n_pad, ld, alpha, nullptr, 0, st);
+  if (!e && quad) e = large_dot_sq(alpha, n_pad, quad, st);
+  if (!e) {
+    // backward half only (forward already applied): reuse potrs with a zero-length forward by
+    // running the backward sweep directly
+    e = large_potrs_backward(a, n_pad, ld, alpha, st);
+  }
+  return e ? cuda_fail(e, "cgp_large_solve_dev") : 0;
+}
+
+int cgp_trsm_rows_dev(const double* a, int64_t n_pad, int64_t ld, double* v, int64_t ldv, int64_t rows, void* stream) {
+  if (!a || !v || rows <= 0 || rows % 128 || n_pad % 128 || ldv < n_pad) return fail(CGP_ERR_ARG, "cgp_trsm_rows_dev: bad arguments");
+  int e = large_trsm_rows(a, n_pad, ld, v, ldv, rows, (cudaStream_t)stream);
+  return e ? cuda_fail(e, "cgp_trsm_rows_dev") : 0;
+}
+
+int cgp_gemm_nt_dev(const double* a, int64_t lda, const double* b, int64_t ldb, double* c, int64_t ldc,
+                    int64_t m, int64_t n, int64_t k, double alpha, double beta, int lower_only, void* stream) {
+  if (!a || !b || !c) return fail(CGP_ERR_ARG, "cgp_gemm_nt_dev: NULL argument");
+  if (m % 128 || n % 128 || k % 16 || m <= 0 || n <= 0 || k <= 0 || lda % 2 || ldb % 2 || ldc % 2)
+    return fail(CGP_ERR_ARG, "cgp_gemm_nt_dev: m, n must be multiples of 128, k of 16, leading dimensions even");
+  GemmArgs g; g.a = a; g.b = b; g.c = c; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.m = (int)m; g.n = (int)n; g.k = (int)k; g.alpha = alpha; g.beta = beta; g.lower_only = lower_only;
+  int e = launch_gemm_nt(g, (cudaStream_t)stream);
+  return e ? cuda_fail(e, "cgp_gemm_nt_dev") : 0;
+}
+
+int cgp_large_predict_dev(const double* a, int64_t n, int64_t n_pad, int64_t ld, int dim, const double* x,
+                          const double* alpha, const double* hyp, double nugget, unsigned flags,
+                          const double* xnew, int64_t m, const double* new_y0, double* mean, double* var,
+                          double* vwork, int64_t chunk_rows, void* stream) {
+  if (!a || !x || !alpha || !xnew || !mean || m < 0) return fail(CGP_ERR_ARG, "cgp_large_predict_dev: NULL argument");
+  if (var && (!vwork || chunk_rows <= 0 || chunk_rows % 128)) return fail(CGP_ERR_ARG, "cgp_large_predict_dev: vwork / chunk_rows (multiple of 128) required for var");
+  cudaStream_t st = (cudaStream_t)stream;
+  Cov c; int rc = make_cov(dim, hyp, nugget, 0.0, flags, &c);
+  if (rc) return rc;
+  int e = large_stream_mean(dim, c, x, alpha, n, xnew, new_y0, m, mean, st);
+  if (e) return cuda_fail(e, "cgp_large_predict_dev (mean)");
+  if (!var) return 0;
+  const double amp_star = c.amp_auto + c.nugget2;
+  for (int64_t r0 = 0; r0 < m; r0 += chunk_rows) {
+    const int64_t rows = m - r0 < chunk_rows ? m - r0 : chunk_rows;
+    const int64_t rows_pad = (rows + 127) / 128 * 128;
+    e = large_cov_build(dim, c, 0, x, n, xnew + r0 * dim, rows, nullptr, vwork, n_pad, rows_pad, n_pad, st);
+    if (!e) e = large_trsm_rows(a, n_pad, ld, vwork, n_pad, rows_pad, st);
+    if (!e) e = large_row_var(vwork, n_pad, n_pad, rows, amp_star, var + r0, st);
+    if (e) return cuda_fail(e, "cgp_large_predict_dev (var)");
+  }
+  return 0;
 }
 
 }  // extern "C"

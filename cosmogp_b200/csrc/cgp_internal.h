@@ -45,7 +45,35 @@ struct SmallArgs {
   // TASK_MATRICES
   const int64_t* moff;
   double* kmat; double* kinv;
+  double* linv;            // L^-1 (lower, zeros above), row-major, same offsets as kmat / kinv
+  int64_t mld;             // leading dimension of the matrix outputs (0 -> N of the object)
+  // matrix source: when non-null the covariance of object b is READ from amat + aoff[b] (row-major,
+  // leading dimension lda, lower triangle) instead of being generated from x (blocked large-object path)
+  const double* amat; const int64_t* aoff; int64_t lda;
+  double* logdet;          // TASK_MATRICES: sum of log pivots per object (may be null)
 };
+
+struct GemmArgs {          // C[m x n] = beta*C + alpha * A[m x k] * B[n x k]^T, all row-major
+  const double* a; const double* b; double* c;
+  int64_t lda, ldb, ldc;
+  int m, n, k;             // multiples of 128 / 128 / 16
+  double alpha, beta;
+  int lower_only;          // 1: only tiles with row-block >= col-block (SYRK on the lower triangle)
+};
+int launch_gemm_nt(const GemmArgs& g, cudaStream_t stream);
+
+// large-object building blocks (cgp_large.cu); all return cudaError_t as int
+int large_cov_build(int dim, const Cov& cov, int autocov, const double* xc, int64_t n, const double* xr, int64_t m,
+                    const double* yerr, double* out, int64_t ld, int64_t rows_pad, int64_t cols_pad, cudaStream_t st);
+int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* info_out, cudaStream_t st);
+int large_potrs(const double* a, int64_t n_pad, int64_t ld, double* v, double* z_out, int backward, cudaStream_t st);
+int large_potrs_backward(const double* a, int64_t n_pad, int64_t ld, double* v, cudaStream_t st);
+int large_trsm_rows(const double* a, int64_t n_pad, int64_t ld, double* v, int64_t ldv, int64_t rows, cudaStream_t st);
+int large_stream_mean(int dim, const Cov& cov, const double* x, const double* alpha, int64_t n,
+                      const double* xnew, const double* new_y0, int64_t m, double* mean, cudaStream_t st);
+int large_row_var(const double* v, int64_t ldv, int64_t n_pad, int64_t rows, double amp_star, double* var, cudaStream_t st);
+int large_dot_sq(const double* v, int64_t n, double* out, cudaStream_t st);
+int large_residual(const double* y, const double* y0, int64_t n, int64_t n_pad, double* r, cudaStream_t st);
 
 // Launchers (cgp_small.cu).  max_n = largest object in the batch.  Return cudaError_t as int.
 int launch_small(Task task, int dim, int max_n, const SmallArgs& a, cudaStream_t stream);

@@ -1,0 +1,471 @@
+// Large single objects (N > 224, e.g. 2D PSF fits with 2,000..20,000 stars): the covariance
+// lives in HBM and is factorised by a right-looking BLOCKED Cholesky with 128-wide panels.
+//   diagonal block  : one CTA, the shared-memory DMMA kernel of cgp_small.cu in matrix-source
+//                     mode -> T_kk = L_kk^-1 (stored in place of the block) + log det
+//   panel           : L_ik = A_ik T_kk^T            (gemm_nt, in place)
+//   trailing update : A_ij -= L_ik L_jk^T, i >= j   (gemm_nt, lower tiles only)  <- N^3/3 of the work
+// gemm_nt is a 128x128x16 double-buffered (cp.async) FP64 tensor-core GEMM: 8 warps, each
+// 32x64 of C as 32 m8n8k4 DMMA accumulators; operands staged in shared memory with a
+// 20-double row pitch so the per-lane fragment loads are bank-conflict free.
+// Reference path replaced: scipy.linalg.cholesky / inv / dot in cosmogp/inv_matrix.py:21-31 and
+// the H K^-1 products of cosmogp/Gaussian_process.py:332-361.
+#include "cgp_internal.h"
+#include "cgp_math.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace cgp {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, PITCH = BK + 4;   // PITCH % 16 == 4 -> conflict-free LDS.64
+constexpr int GEMM_THREADS = 256;
+constexpr size_t GEMM_SMEM = (size_t)2 * (BM + BN) * PITCH * sizeof(double);
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_nt_kernel(const GemmArgs g) {
+  extern __shared__ __align__(16) double sm[];
+  double* As = sm;                                 // [2][BM][PITCH]
+  double* Bs = sm + 2 * BM * PITCH;                // [2][BN][PITCH]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;         // 4 x 2 warps: 32 x 64 of C each
+
+  int bi, bj;
+  if (g.lower_only) {                              // linear index -> (bi, bj), bi >= bj
+    const int t = blockIdx.x;
+    bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    while (bi * (bi + 1) / 2 > t) --bi;
+    bj = t - bi * (bi + 1) / 2;
+  } else {
+    const int nbn = g.n / BN;
+    bi = blockIdx.x / nbn; bj = blockIdx.x - bi * nbn;
+  }
+  const double* ga = g.a + (int64_t)bi * BM * g.lda;
+  const double* gb = g.b + (int64_t)bj * BN * g.ldb;
+
+  auto load_stage = [&](int st, int kc) {
+    double* as = As + st * BM * PITCH;
+    double* bs = Bs + st * BN * PITCH;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = tid + i * GEMM_THREADS;        // 1024 16-byte pieces per operand
+      const int row = p >> 3, c2 = (p & 7) << 1;
+      cp_async16(as + row * PITCH + c2, ga + (int64_t)row * g.lda + kc * BK + c2);
+      cp_async16(bs + row * PITCH + c2, gb + (int64_t)row * g.ldb + kc * BK + c2);
+    }
+    cp_async_commit();
+  };
+
+  double acc0[4][8], acc1[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc0[i][j] = 0.0; acc1[i][j] = 0.0; }
+
+  const int nk = g.k / BK;
+  load_stage(0, 0);
+  for (int kc = 0; kc < nk; ++kc) {
+    const int st = kc & 1;
+    if (kc + 1 < nk) { load_stage(st ^ 1, kc + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const double* as = As + st * BM * PITCH + (wm * 32 + gq) * PITCH + tq;
+    const double* bs = Bs + st * BN * PITCH + (wn * 64 + gq) * PITCH + tq;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ++ks) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = as[i * 8 * PITCH + ks * 4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bf[j] = bs[j * 8 * PITCH + ks * 4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma(acc0[i][j], acc1[i][j], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+
+  double* gc = g.c + ((int64_t)bi * BM + wm * 32 + gq) * g.ldc + (int64_t)bj * BN + wn * 64 + 2 * tq;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double2* p = reinterpret_cast<double2*>(gc + (int64_t)i * 8 * g.ldc + j * 8);
+      double2 v = make_double2(g.alpha * acc0[i][j], g.alpha * acc1[i][j]);
+      if (g.beta != 0.0) { const double2 o = *p; v.x = fma(g.beta, o.x, v.x); v.y = fma(g.beta, o.y, v.y); }
+      *p = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Covariance builder: out[r][c] = amp * exp(-q(row point r, col point c)/2) (+ noise on the
+// diagonal of an auto-covariance; identity padding beyond n / m).  One thread per 2 columns,
+// coalesced 16-byte stores; the write (8 B/entry) and the exp (15 FP64 ops) bound it.
+struct CovArgs {
+  int dim; Cov cov; int autocov;
+  const double* xc; int64_t n;          // column points (the object's epochs / stars)
+  const double* xr; int64_t m;          // row points (== xc for auto-covariance)
+  const double* yerr;
+  double* out; int64_t ld; int64_t rows_pad, cols_pad;
+};
+
+template <int DIM>
+__global__ void cov_build_kernel(const CovArgs a) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int64_t r = blockIdx.y;
+  if (c >= a.cols_pad) return;
+  double rx = 0.0, ry = 0.0;
+  const bool rin = r < a.m;
+  if (rin) { if (DIM == 1) rx = a.xr[r]; else { rx = a.xr[2 * r]; ry = a.xr[2 * r + 1]; } }
+  double v[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int64_t cc = c + e;
+    double val = 0.0;
+    if (rin && cc < a.n) {
+      double cx, cy = 0.0;
+      if (DIM == 1) cx = a.xc[cc]; else { cx = a.xc[2 * cc]; cy = a.xc[2 * cc + 1]; }
+      const double dx = cx - rx;                  // kernel.py:71: A = x - x2[:,None]
+      double arg;
+      if (DIM == 1) arg = dx * dx * a.cov.h00;
+      else { const double dy = cy - ry; arg = fma(dy * a.cov.h11, dy, fma(dx, a.cov.h00, dy * a.cov.h01) * dx); }
+      val = (a.autocov ? a.cov.amp_auto : a.cov.amp_cross) * cgp_exp(arg);
+    }
+    if (a.autocov && cc == r) {
+      if (rin) { const double ye = a.yerr ? a.yerr[r] : 0.0; val = a.cov.amp_auto + ye * ye + a.cov.noise_const; }
+      else val = 1.0;                              // identity padding keeps the factorisation valid
+    }
+    v[e] = val;
+  }
+  double* p = a.out + r * a.ld + c;
+  if (c + 1 < a.cols_pad) *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  else p[0] = v[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// Triangular solves against the blocked factor (diagonal blocks hold T = L_kk^-1).
+// w_k <- T_kk v_k  (or T_kk^T v_k): one CTA of 128 threads, one row each.
+__global__ void __launch_bounds__(128) diag_apply_kernel(const double* a, int64_t ld, int64_t k0, double* v, int trans) {
+  __shared__ double s[128];
+  const int i = threadIdx.x;
+  s[i] = v[k0 + i];
+  __syncthreads();
+  const double* t = a + k0 * ld + k0;
+  double acc = 0.0;
+  if (!trans) { for (int c = 0; c <= i; ++c) acc = fma(t[(int64_t)i * ld + c], s[c], acc); }
+  else { for (int c = i; c < 128; ++c) acc = fma(t[(int64_t)c * ld + i], s[c], acc); }
+  __syncthreads();
+  v[k0 + i] = acc;
+}
+// forward sweep: v[rows > k] -= L[rows, k-block] z_k.  One warp per row, 4 columns per lane.
+__global__ void __launch_bounds__(256) panel_gemv_sub_kernel(const double* a, int64_t ld, int64_t k0, int64_t n_pad, double* v) {
+  __shared__ double s[128];
+  if (threadIdx.x < 128) s[threadIdx.x] = v[k0 + threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = k0 + 128 + (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  const double* p = a + row * ld + k0 + lane * 4;
+  const double2 u0 = *reinterpret_cast<const double2*>(p), u1 = *reinterpret_cast<const double2*>(p + 2);
+  double acc = u0.x * s[lane * 4] + u0.y * s[lane * 4 + 1] + u1.x * s[lane * 4 + 2] + u1.y * s[lane * 4 + 3];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) v[row] -= acc;
+}
+// backward sweep: v[cols < k] -= L[k-block, cols]^T alpha_k.  One thread per column.
+__global__ void __launch_bounds__(128) panel_gemvT_sub_kernel(const double* a, int64_t ld, int64_t k0, double* v) {
+  __shared__ double s[128];
+  s[threadIdx.x] = v[k0 + threadIdx.x];
+  __syncthreads();
+  const int64_t col = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (col >= k0) return;
+  const double* p = a + k0 * ld + col;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int r = 0; r < 128; ++r) acc = fma(p[(int64_t)r * ld], s[r], acc);
+  v[col] -= acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// Prediction epilogues.
+// mean[m] = amp_cross * sum_n exp(-q(m,n)/2) alpha_n + y0*[m]  -- cross-covariance never stored.
+template <int DIM>
+__global__ void __launch_bounds__(256) stream_mean_kernel(const Cov cov, const double* x, const double* alpha, int64_t n,
+                                                          const double* xnew, const double* new_y0, int64_t m, double* mean) {
+  extern __shared__ double sh[];
+  double* sx = sh; double* sy = sh + 1024; double* sa = sh + (DIM == 2 ? 2048 : 1024);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double gx = 0.0, gy = 0.0;
+  if (i < m) { if (DIM == 1) gx = xnew[i]; else { gx = xnew[2 * i]; gy = xnew[2 * i + 1]; } }
+  double acc = 0.0, acc2 = 0.0;
+  for (int64_t c0 = 0; c0 < n; c0 += 1024) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) {
+      const int64_t c = c0 + j;
+      const bool in = c < n;
+      if (DIM == 1) sx[j] = in ? x[c] : 0.0; else { sx[j] = in ? x[2 * c] : 0.0; sy[j] = in ? x[2 * c + 1] : 0.0; }
+      sa[j] = in ? alpha[c] : 0.0;                  // zero weight beyond n
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < 1024; j += 2) {
+      double a0, a1;
+      {
+        const double dx = sx[j] - gx;
+        if (DIM == 1) a0 = dx * dx * cov.h00;
+        else { const double dy = sy[j] - gy; a0 = fma(dy * cov.h11, dy, fma(dx, cov.h00, dy * cov.h01) * dx); }
+      }
+      {
+        const double dx = sx[j + 1] - gx;
+        if (DIM == 1) a1 = dx * dx * cov.h00;
+        else { const double dy = sy[j + 1] - gy; a1 = fma(dy * cov.h11, dy, fma(dx, cov.h00, dy * cov.h01) * dx); }
+      }
+      acc = fma(cgp_exp(a0), sa[j], acc); acc2 = fma(cgp_exp(a1), sa[j + 1], acc2);
+    }
+  }
+  if (i < m) mean[i] = fma(cov.amp_cross, acc + acc2, new_y0 ? new_y0[i] : 0.0);
+}
+// var[m] = amp* - |v_m|^2 with v_m = row m of V (mc x n_pad): one warp per row.
+__global__ void __launch_bounds__(256) row_norm_var_kernel(const double* v, int64_t ld, int64_t n_pad, int64_t rows,
+                                                           double amp_star, double* var) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const double* p = v + r * ld;
+  double acc = 0.0, acc2 = 0.0;
+  for (int64_t c = lane * 2; c < n_pad; c += 64) {
+    const double2 u = *reinterpret_cast<const double2*>(p + c);
+    acc = fma(u.x, u.x, acc); acc2 = fma(u.y, u.y, acc2);
+  }
+  acc += acc2;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) var[r] = amp_star - acc;
+}
+__global__ void dot_sq_kernel(const double* v, int64_t n, double* out) {      // out[0] = |v|^2 (one CTA)
+  __shared__ double s[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], v[i], acc);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) out[0] = acc;
+  }
+}
+__global__ void sum_kernel(const double* v, int64_t n, double* out) {         // out[0] = sum v (one CTA, fixed order)
+  __shared__ double s[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) out[0] = acc;
+  }
+}
+__global__ void potrf_setup_kernel(int64_t* blk_off, int64_t* blk_aoff, int nblk, int64_t ld) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) { blk_off[0] = 0; blk_off[1] = 128; }
+  if (k < nblk) blk_aoff[k] = (int64_t)k * 128 * ld + (int64_t)k * 128;
+}
+__global__ void potrf_finish_kernel(const double* ld_blocks, const int* info_blocks, int nblk, double* logdet, int* info) {
+  if (threadIdx.x == 0) {
+    double s = 0.0; int bad = 0;
+    for (int k = 0; k < nblk; ++k) { s += ld_blocks[k]; if (!bad && info_blocks[k]) bad = k * 128 + info_blocks[k]; }
+    if (logdet) *logdet = bad ? nan("") : s;
+    if (info) *info = bad;
+  }
+}
+__global__ void residual_kernel(const double* y, const double* y0, int64_t n, int64_t n_pad, double* r) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) r[i] = i < n ? y[i] - (y0 ? y0[i] : 0.0) : 0.0;
+}
+
+}  // namespace
+
+// =========================================================================================
+int launch_gemm_nt(const GemmArgs& g, cudaStream_t stream) {
+  if (g.m % BM || g.n % BN || g.k % BK || g.m <= 0 || g.n <= 0 || g.k <= 0) return (int)cudaErrorInvalidValue;
+  static bool init = false;
+  if (!init) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    init = true;
+  }
+  const int64_t tm = g.m / BM, tn = g.n / BN;
+  const int64_t tiles = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  gemm_nt_kernel<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM, stream>>>(g);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int large_cov_build(int dim, const Cov& cov, int autocov, const double* xc, int64_t n, const double* xr, int64_t m,
+                    const double* yerr, double* out, int64_t ld, int64_t rows_pad, int64_t cols_pad, cudaStream_t st) {
+  CovArgs a;
+  a.dim = dim; a.cov = cov; a.autocov = autocov; a.xc = xc; a.n = n; a.xr = xr; a.m = m; a.yerr = yerr;
+  a.out = out; a.ld = ld; a.rows_pad = rows_pad; a.cols_pad = cols_pad;
+  if (rows_pad <= 0 || cols_pad <= 0) return 0;
+  if (rows_pad > 2147483647) return (int)cudaErrorInvalidValue;
+  dim3 grid((unsigned)((cols_pad / 2 + 1 + 127) / 128), 1);
+  // grid.y is limited to 65535: sweep the rows in slabs
+  for (int64_t r0 = 0; r0 < rows_pad; r0 += 65535) {
+    CovArgs s = a;
+    const int64_t rows = rows_pad - r0 < 65535 ? rows_pad - r0 : 65535;
+    s.out = out + r0 * ld;
+    s.xr = xr + r0 * dim;
+    s.m = m - r0 > 0 ? m - r0 : 0;
+    s.rows_pad = rows;
+    if (autocov) {                                  // diagonal test uses absolute indices: shift the columns instead
+      // (auto-covariances larger than 65535 rows are built slab by slab with a column origin)
+      if (r0) return (int)cudaErrorInvalidValue;
+    }
+    grid.y = (unsigned)rows;
+    if (dim == 1) cov_build_kernel<1><<<grid, 128, 0, st>>>(s); else cov_build_kernel<2><<<grid, 128, 0, st>>>(s);
+    count_launch();
+  }
+  return (int)cudaGetLastError();
+}
+
+// In-place blocked Cholesky of the lower triangle of a (n_pad x n_pad, n_pad % 128 == 0).
+// On exit: strictly-lower 128-blocks = L, diagonal blocks = (L_kk)^-1 with zeros above the
+// diagonal, logdet_blocks[k] = sum log pivots of block k, info_blocks[k] = failing pivot (0 = ok).
+int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* info_out, cudaStream_t st) {
+  const int nblk = (int)(n_pad / 128);
+  // stream-ordered scratch: per-block log det / info and the two tiny CSR arrays the block kernel reads
+  char* scratch = nullptr;
+  const size_t bytes = (size_t)nblk * (sizeof(double) + sizeof(int) + sizeof(int64_t)) + 4 * sizeof(int64_t) + 64;
+  cudaError_t ce = cudaMallocAsync((void**)&scratch, bytes, st);
+  if (ce != cudaSuccess) return (int)ce;
+  double* logdet_blocks = (double*)scratch;
+  int64_t* blk_aoff = (int64_t*)(scratch + (size_t)nblk * sizeof(double));
+  int64_t* blk_off = blk_aoff + nblk;
+  int* info_blocks = (int*)(blk_off + 2);
+  potrf_setup_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(blk_off, blk_aoff, nblk, ld);
+  count_launch();
+  int rc = 0;
+  for (int k = 0; k < nblk; ++k) {
+    const int64_t k0 = (int64_t)k * 128;
+    SmallArgs s; memset(&s, 0, sizeof s);
+    s.n_obj = 1; s.off = blk_off;                  // {0, 128}
+    s.amat = a; s.aoff = blk_aoff + k; s.lda = ld;
+    s.moff = blk_aoff + k; s.mld = ld; s.linv = a;
+    s.logdet = logdet_blocks + k; s.info = info_blocks + k;
+    s.cov.amp_auto = 1.0; s.cov.amp_cross = 1.0;
+    int e = launch_small(TASK_MATRICES, 1, 128, s, st);
+    if (e) { rc = e; break; }
+    const int64_t rest = n_pad - k0 - 128;
+    if (rest <= 0) break;
+    GemmArgs p;                                      // panel: L_ik = A_ik T_kk^T (in place, one tile column)
+    p.a = a + (k0 + 128) * ld + k0; p.lda = ld;
+    p.b = a + k0 * ld + k0; p.ldb = ld;
+    p.c = a + (k0 + 128) * ld + k0; p.ldc = ld;
+    p.m = (int)rest; p.n = 128; p.k = 128; p.alpha = 1.0; p.beta = 0.0; p.lower_only = 0;
+    if ((e = launch_gemm_nt(p, st))) { rc = e; break; }
+    GemmArgs u;                                      // trailing update on the lower triangle
+    u.a = p.c; u.lda = ld; u.b = p.c; u.ldb = ld;
+    u.c = a + (k0 + 128) * ld + (k0 + 128); u.ldc = ld;
+    u.m = (int)rest; u.n = (int)rest; u.k = 128; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+    if ((e = launch_gemm_nt(u, st))) { rc = e; break; }
+  }
+  potrf_finish_kernel<<<1, 32, 0, st>>>(logdet_blocks, info_blocks, nblk, logdet_out, info_out);
+  count_launch();
+  cudaFreeAsync(scratch, st);
+  return rc ? rc : (int)cudaGetLastError();
+}
+
+// v <- L^-1 v (forward) then, if backward, v <- L^-T v.  z_out (optional) receives L^-1 v.
+int large_potrs(const double* a, int64_t n_pad, int64_t ld, double* v, double* z_out, int backward, cudaStream_t st) {
+  const int nblk = (int)(n_pad / 128);
+  for (int k = 0; k < nblk; ++k) {
+    const int64_t k0 = (int64_t)k * 128;
+    diag_apply_kernel<<<1, 128, 0, st>>>(a, ld, k0, v, 0);
+    const int64_t rest = n_pad - k0 - 128;
+    if (rest > 0) panel_gemv_sub_kernel<<<(unsigned)((rest + 7) / 8), 256, 0, st>>>(a, ld, k0, n_pad, v);
+    count_launch(rest > 0 ? 2 : 1);
+  }
+  if (z_out) cudaMemcpyAsync(z_out, v, n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  if (backward) return large_potrs_backward(a, n_pad, ld, v, st);
+  return (int)cudaGetLastError();
+}
+
+int large_potrs_backward(const double* a, int64_t n_pad, int64_t ld, double* v, cudaStream_t st) {
+  const int nblk = (int)(n_pad / 128);
+  for (int k = nblk - 1; k >= 0; --k) {
+    const int64_t k0 = (int64_t)k * 128;
+    diag_apply_kernel<<<1, 128, 0, st>>>(a, ld, k0, v, 1);
+    if (k0 > 0) panel_gemvT_sub_kernel<<<(unsigned)(k0 / 128), 128, 0, st>>>(a, ld, k0, v);
+    count_launch(k0 > 0 ? 2 : 1);
+  }
+  return (int)cudaGetLastError();
+}
+
+// V (rows x n_pad, row-major, leading dimension ldv) holds cross-covariance rows h_m on entry
+// and v_m = L^-1 h_m on exit: blocked left-looking solve, all FLOPs in gemm_nt.  rows % 128 == 0.
+int large_trsm_rows(const double* a, int64_t n_pad, int64_t ld, double* v, int64_t ldv, int64_t rows, cudaStream_t st) {
+  const int nblk = (int)(n_pad / 128);
+  for (int k = 0; k < nblk; ++k) {
+    const int64_t k0 = (int64_t)k * 128;
+    int e;
+    if (k > 0) {                                     // V[:,k] -= V[:,0:k] L[k,0:k]^T
+      GemmArgs u;
+      u.a = v; u.lda = ldv; u.b = a + k0 * ld; u.ldb = ld; u.c = v + k0; u.ldc = ldv;
+      u.m = (int)rows; u.n = 128; u.k = (int)k0; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 0;
+      if ((e = launch_gemm_nt(u, st))) return e;
+    }
+    GemmArgs p;                                      // V[:,k] = V[:,k] T_kk^T
+    p.a = v + k0; p.lda = ldv; p.b = a + k0 * ld + k0; p.ldb = ld; p.c = v + k0; p.ldc = ldv;
+    p.m = (int)rows; p.n = 128; p.k = 128; p.alpha = 1.0; p.beta = 0.0; p.lower_only = 0;
+    if ((e = launch_gemm_nt(p, st))) return e;
+  }
+  return 0;
+}
+
+int large_stream_mean(int dim, const Cov& cov, const double* x, const double* alpha, int64_t n,
+                      const double* xnew, const double* new_y0, int64_t m, double* mean, cudaStream_t st) {
+  if (m <= 0) return 0;
+  const unsigned grid = (unsigned)((m + 255) / 256);
+  if (dim == 1) stream_mean_kernel<1><<<grid, 256, 2 * 1024 * sizeof(double), st>>>(cov, x, alpha, n, xnew, new_y0, m, mean);
+  else stream_mean_kernel<2><<<grid, 256, 3 * 1024 * sizeof(double), st>>>(cov, x, alpha, n, xnew, new_y0, m, mean);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+int large_row_var(const double* v, int64_t ldv, int64_t n_pad, int64_t rows, double amp_star, double* var, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  row_norm_var_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(v, ldv, n_pad, rows, amp_star, var);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+int large_dot_sq(const double* v, int64_t n, double* out, cudaStream_t st) {
+  dot_sq_kernel<<<1, 1024, 0, st>>>(v, n, out); count_launch(); return (int)cudaGetLastError();
+}
+int large_sum(const double* v, int64_t n, double* out, cudaStream_t st) {
+  sum_kernel<<<1, 1024, 0, st>>>(v, n, out); count_launch(); return (int)cudaGetLastError();
+}
+int large_residual(const double* y, const double* y0, int64_t n, int64_t n_pad, double* r, cudaStream_t st) {
+  residual_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(y, y0, n, n_pad, r); count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace cgp

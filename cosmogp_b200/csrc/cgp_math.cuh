@@ -8,7 +8,7 @@ namespace cgp {
 
 // Literal doubles cost two 32-bit immediate moves per use; from constant memory they are a
 // direct DFMA operand (c[bank][off]).
-__constant__ double kExp[16] = {
+static __constant__ double kExp[16] = {
     1.4426950408889634, 6755399441055744.0, -6.93147180559945286e-01, -2.31904681384629956e-17,
     2.5110049204818658e-08, 2.763265472252779e-07, 2.755724088722987e-06, 2.4801485441561313e-05,
     0.00019841269890076403, 0.0013888888952352863, 0.008333333333319589, 0.04166666666648795,

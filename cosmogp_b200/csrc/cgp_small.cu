@@ -132,8 +132,16 @@ __device__ __forceinline__ double cov_e(const Cov& c, const double* px, int ld, 
 template <int DIM>
 __device__ __forceinline__ void k_tile_minus(const Cov& cov, const double* px, const double* noise, int ld, int n,
                                              int I, int J, const Lane& L, double s0, double s1,
-                                             double& k0, double& k1) {
+                                             double& k0, double& k1, const double* amat = nullptr, int64_t lda = 0) {
   const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
+  if (amat) {                                             // covariance supplied in HBM (lower triangle)
+    k0 = -s0; k1 = -s1;
+    if (gi < n && cj <= gi) k0 += amat[(int64_t)gi * lda + cj];
+    if (gi < n && cj + 1 <= gi) k1 += amat[(int64_t)gi * lda + cj + 1];
+    if (gi >= n && cj == gi) k0 = 1.0 - s0;
+    if (gi >= n && cj + 1 == gi) k1 = 1.0 - s1;
+    return;
+  }
   double e0 = 0.0, e1 = 0.0;
   if (gi < n && cj < gi) e0 = cov_e<DIM>(cov, px, ld, gi, cj);
   if (gi < n && cj + 1 < gi) e1 = cov_e<DIM>(cov, px, ld, gi, cj + 1);
@@ -177,17 +185,20 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
     const int64_t o0 = a.off[b];
     const int n = (int)(a.off[b + 1] - o0);
     const int nb = (n + 7) >> 3;
+    const double* amat = a.amat ? a.amat + a.aoff[b] : nullptr;
 
     // ---------------- stage the object
     cta_sync<WARPS>();                                    // previous object fully consumed
     double rsum = 0.0;
     for (int i = tid; i < 8 * nb; i += NT) {
       const bool in = i < n;
-      if (DIM == 1) {
-        px[i] = in ? a.x[o0 + i] : 0.0;
-      } else {
-        px[i] = in ? a.x[2 * (o0 + i)] : 0.0;
-        px[ld + i] = in ? a.x[2 * (o0 + i) + 1] : 0.0;
+      if (!amat) {
+        if (DIM == 1) {
+          px[i] = in ? a.x[o0 + i] : 0.0;
+        } else {
+          px[i] = in ? a.x[2 * (o0 + i)] : 0.0;
+          px[ld + i] = in ? a.x[2 * (o0 + i) + 1] : 0.0;
+        }
       }
       const double ye = (in && a.yerr) ? a.yerr[o0 + i] : 0.0;
       noise[i] = ye * ye + cov.noise_const;
@@ -225,12 +236,12 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
           dmma(c0, c1, fc.x, fb.x); dmma(d0, d1, fc.y, fb.y);
         }
         double k0, k1;
-        k_tile_minus<DIM>(cov, px, noise, ld, n, I, J, L, a0 + b0, a1 + b1, k0, k1);
+        k_tile_minus<DIM>(cov, px, noise, ld, n, I, J, L, a0 + b0, a1 + b1, k0, k1, amat, a.lda);
         if (I == J) {                                     // warp 0
           double t0, t1, piv; int badk;
           diag_factor(k0, k1, L, t0, t1, piv, badk);
           st_acc(tiles, slot(J, J), L, t0, t1);
-          if (TASK == TASK_LL) {
+          if (TASK == TASK_LL || TASK == TASK_MATRICES) {
             lp_m *= piv;
             const int hi = __double2hiint(lp_m);
             const int e = ((hi >> 20) & 0x7ff) - 1023;
@@ -242,7 +253,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
           st_acc(tiles, slot(I, J), L, k0, k1);           // park C[I][J] in its own slot
         }
         if (two) {
-          k_tile_minus<DIM>(cov, px, noise, ld, n, I2, J, L, c0 + d0, c1 + d1, k0, k1);
+          k_tile_minus<DIM>(cov, px, noise, ld, n, I2, J, L, c0 + d0, c1 + d1, k0, k1, amat, a.lda);
           st_acc(tiles, slot(I2, J), L, k0, k1);
         }
       }
@@ -331,13 +342,30 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
 
     if (TASK == TASK_MATRICES) {
       const int bad = s_bad;
-      if (tid == 0) a.info[b] = bad;
+      if (tid == 0) {
+        a.info[b] = bad;
+        if (a.logdet) a.logdet[b] = bad ? nan("") : log(lp_m) + (double)lp_e * 0.693147180559945309417232;
+      }
       const int64_t mo = a.moff[b];
-      if (a.kmat) {
+      const int64_t mld = a.mld ? a.mld : n;
+      if (a.kmat && !amat) {
         for (int e = tid; e < n * n; e += NT) {
           const int i = e / n, j = e - i * n;
-          a.kmat[mo + e] = (i == j) ? cov.amp_auto + noise[i] : cov.amp_auto * cov_e<DIM>(cov, px, ld, i, j);
+          a.kmat[mo + (int64_t)i * mld + j] = (i == j) ? cov.amp_auto + noise[i] : cov.amp_auto * cov_e<DIM>(cov, px, ld, i, j);
         }
+      }
+      if (a.linv) {       // L^-1 tiles (lower) and explicit zeros above the diagonal
+        int q = 0;
+        for (int I = 0; I < nb; ++I)
+          for (int J = 0; J < nb; ++J, ++q) {
+            if (q % WARPS != warp) continue;
+            const double* tp = tiles + slot(I, J <= I ? J : 0) * TILE;
+            const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
+            double c0 = (J <= I) ? tp[L.st0] : 0.0, c1 = (J <= I) ? tp[L.st1] : 0.0;
+            if (bad) { c0 = nan(""); c1 = c0; }
+            if (gi < n && cj < n) a.linv[mo + (int64_t)gi * mld + cj] = c0;
+            if (gi < n && cj + 1 < n) a.linv[mo + (int64_t)gi * mld + cj + 1] = c1;
+          }
       }
       if (a.kinv) {       // K^-1 = L^-T L^-1: tile (I,J) = sum_{P>=I} Linv[P][I]^T Linv[P][J]
         int q = 0;
@@ -353,8 +381,8 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
             if (bad) { c0 = nan(""); c1 = c0; }
             const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
             if (gi < n) {
-              if (cj < n) { a.kinv[mo + (int64_t)gi * n + cj] = c0; a.kinv[mo + (int64_t)cj * n + gi] = c0; }
-              if (cj + 1 < n) { a.kinv[mo + (int64_t)gi * n + cj + 1] = c1; a.kinv[mo + (int64_t)(cj + 1) * n + gi] = c1; }
+              if (cj < n) { a.kinv[mo + (int64_t)gi * mld + cj] = c0; a.kinv[mo + (int64_t)cj * mld + gi] = c0; }
+              if (cj + 1 < n) { a.kinv[mo + (int64_t)gi * mld + cj + 1] = c1; a.kinv[mo + (int64_t)(cj + 1) * mld + gi] = c1; }
             }
           }
       }

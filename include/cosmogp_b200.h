@@ -114,6 +114,53 @@ int cgp_matrices_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int d
                              const double* hyp, double nugget, double floor, unsigned flags,
                              const int64_t* moff, double* kmat, double* kinv, int* info, void* stream);
 
+/* ======================================================================================
+ * Large single objects (N > CGP_SMALL_MAX_N; BASELINE configs 3 and 4) and the per-matrix
+ * operator seams.  The covariance lives in HBM in a caller-provided (n_pad x n_pad) row-major
+ * buffer, n_pad = cgp_pad128(n); rows/columns beyond n are identity padding.
+ * ==================================================================================== */
+int64_t cgp_pad128(int64_t n);
+
+/* kernel(x, hyp, new_x, nugget, floor, y_err) -- the kernel-callable seam of
+ * cosmogp/Gaussian_process.py:136-154 (cosmogp/kernel.py:25-77, 80-155).
+ * xnew == NULL: auto-covariance, out is (rows_pad x cols_pad) >= (n x n) with the noise diagonal
+ * (and identity padding); else cross-covariance K(xnew, x) of shape (m x n), zero padding. */
+int cgp_cov_matrix_dev(int dim, const double* x, int64_t n, const double* xnew, int64_t m,
+                       const double* y_err, const double* hyp, double nugget, double floor, unsigned flags,
+                       double* out, int64_t ld, int64_t rows_pad, int64_t cols_pad, void* stream);
+
+/* Blocked Cholesky, in place on the lower triangle (scipy.linalg.cholesky at
+ * cosmogp/inv_matrix.py:23).  On exit the strictly-lower 128-blocks hold L and each diagonal
+ * 128-block holds inv(L_kk) (zeros above its diagonal).  logdet (device double) = sum 2 log L_ii
+ * (inv_matrix.py:28); info (device int) = 1-based failing pivot or 0. */
+int cgp_potrf_dev(double* a, int64_t n_pad, int64_t ld, double* logdet, int* info, void* stream);
+
+/* v <- L^-1 v, optionally copied to z_out, then (backward != 0) v <- L^-T v. v has n_pad entries. */
+int cgp_potrs_dev(const double* a, int64_t n_pad, int64_t ld, double* v, double* z_out, int backward, void* stream);
+
+/* r = y - y0 (zero padded), z = L^-1 r, *quad = |z|^2 (device double), alpha = K^-1 r.
+ * With cgp_potrf_dev's logdet this is log_likelihood_gp (cosmogp/Gaussian_process.py:68-73):
+ * LL = -(quad + logdet + n log 2 pi)/2. */
+int cgp_large_solve_dev(const double* a, int64_t n, int64_t n_pad, int64_t ld,
+                        const double* y, const double* y0, double* alpha, double* quad, void* stream);
+
+/* Prediction against a factored large object (cosmogp/Gaussian_process.py:332-361, diagonal of
+ * the covariance): mean by a streaming kernel that never stores K(x*,x); var (may be NULL) by a
+ * blocked triangular solve on chunks of `chunk_rows` grid points (multiple of 128) staged in
+ * vwork (chunk_rows x n_pad doubles). */
+int cgp_large_predict_dev(const double* a, int64_t n, int64_t n_pad, int64_t ld, int dim, const double* x,
+                          const double* alpha, const double* hyp, double nugget, unsigned flags,
+                          const double* xnew, int64_t m, const double* new_y0, double* mean, double* var,
+                          double* vwork, int64_t chunk_rows, void* stream);
+
+/* v_m = L^-1 h_m for `rows` rows of V (rows x n_pad, rows % 128 == 0), in place. */
+int cgp_trsm_rows_dev(const double* a, int64_t n_pad, int64_t ld, double* v, int64_t ldv, int64_t rows, void* stream);
+
+/* C[m x n] = beta C + alpha A[m x k] B[n x k]^T on the FP64 tensor pipe; m, n % 128 == 0, k % 16 == 0;
+ * lower_only != 0 computes only the tiles on or below the block diagonal. */
+int cgp_gemm_nt_dev(const double* a, int64_t lda, const double* b, int64_t ldb, double* c, int64_t ldc,
+                    int64_t m, int64_t n, int64_t k, double alpha, double beta, int lower_only, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

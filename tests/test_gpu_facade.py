@@ -1,0 +1,141 @@
+"""The drop-in objects, used the way cosmogp's notebooks and pull.py use the reference
+(gaussian_process / gaussian_process_nobject / build_pull), against the golden fixtures."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, golden, split
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cg():
+    import cosmogp_b200
+    from cosmogp_b200 import _lib
+    _lib.require_device()
+    return cosmogp_b200
+
+
+def test_single_object_workflow(cg):
+    g = golden("kat_1d")
+    gp = cg.gaussian_process(g["y"], g["x"], y_err=g["y_err"])
+    assert_close(gp.hyperparameters, g["init_rbf"], 1e-15)
+    gp.hyperparameters = g["hyp"]; gp.nugget = float(g["nugget"])
+    gp.compute_log_likelihood(g["hyp"], svd_method=False)
+    assert gp.log_likelihood.shape == (1,)
+    assert_close(gp.log_likelihood[0], g["ll_chol"], 1e-9)
+    gp.get_prediction(new_binning=g["grid"], svd_method=False)
+    assert_close(gp.Prediction[0], g["mean"], 1e-9)
+    assert_close(gp.kernel_matrix[0], g["kmat"], 1e-12)
+    assert_close(gp.inv_kernel_matrix[0], g["kinv"], 1e-9, 1e-10)
+    assert_close(gp.covariance_matrix[0], g["cov"], 1e-9, 1e-12)
+    assert_close(gp.prediction_variance[0], np.diag(g["cov"]), 1e-9)
+    with pytest.raises(AssertionError):
+        cg.gaussian_process(g["y"], g["x"], kernel="RBF3D")
+    with pytest.raises(AssertionError):
+        gp.find_hyperparameters(hyperparameter_guess=[1.0])
+
+
+def test_fit_hyperparameters_c1(cg):
+    """find_hyperparameters drives scipy's Nelder-Mead with one device launch per evaluation; the
+    optimum must agree with the reference's to the optimiser's own tolerance (xtol = 1e-4)."""
+    g = golden("c1_single")
+    gp = cg.gaussian_process(g["y"], g["x"], y_err=g["y_err"])
+    gp.find_hyperparameters(hyperparameter_guess=[0.5, 8.0], svd_method=False)
+    assert_close(gp.hyperparameters, g["fit_hyp"], 1e-4)
+    gn = cg.gaussian_process(g["y"], g["x"], y_err=g["y_err"])
+    gn.find_hyperparameters(hyperparameter_guess=[0.5, 8.0], nugget=True, svd_method=False)
+    assert_close(list(gn.hyperparameters) + [gn.nugget], list(g["fit_hyp_nugget"]) + [float(g["fit_nugget"])], 2e-3, 2e-4)
+    gp.hyperparameters = g["hyp"]; gp.nugget = float(g["nugget"])
+    gp.get_prediction(new_binning=g["grid"], COV=True, svd_method=False)
+    assert_close(gp.Prediction[0], g["mean"], 1e-9, 1e-12)
+    cov = gp.covariance_matrix[0]
+    assert cov.shape == (500, 500)
+    assert_close(np.diag(cov), g["cov_diag"], 1e-9, 1e-13)
+    assert_close(cov[100:140, 100:140], g["cov_block"], 1e-9, 1e-12)
+    assert_close(cov.sum(), g["cov_sum"], 1e-8)
+
+
+def test_nobject_shared_mean_workflow(cg):
+    g = golden("ragged_1d")
+    off = g["off"]
+    xs, ys, yes = (split(g[k], off) for k in ("x", "y", "y_err"))
+    gp = cg.gaussian_process_nobject(ys, xs, y_err=yes, Mean_Y=g["mean_y"], Time_mean=g["mean_x"])
+    assert_close(np.concatenate(gp.y0), g["y0"], 1e-15)
+    assert_close(gp.hyperparameters, g["init_rbf"], 1e-15)
+    gp.hyperparameters = g["hyp"].copy()
+    gp.compute_log_likelihood(g["hyp"], svd_method=False)
+    assert_close(gp.log_likelihood[0], g["ll_sum"], 1e-9)
+    assert_close(gp.log_likelihood_per_object, g["ll_obj"], 1e-9)
+    gp.get_prediction(new_binning=g["grid"], svd_method=False)
+    assert_close(np.array(gp.Prediction), g["mean"], 1e-9)
+    assert_close(np.array(gp.prediction_variance), g["var"], 1e-9, 1e-13)
+    assert_close(gp.covariance_matrix[0], g["cov0"], 1e-9, 1e-12)
+    assert_close(gp.kernel_matrix[0], g["kmat0"], 1e-12); assert_close(gp.inv_kernel_matrix[0], g["kinv0"], 1e-9, 1e-9)
+    gf = cg.gaussian_process_nobject(ys, xs, y_err=yes, Mean_Y=g["mean_y"], Time_mean=g["mean_x"])
+    gf.find_hyperparameters(hyperparameter_guess=[0.5, 2.0], svd_method=False)
+    assert_close(gf.hyperparameters, g["fit_hyp"], 1e-4)
+    # own-epoch prediction
+    g1 = cg.gaussian_process(ys[0], xs[0], y_err=yes[0], Mean_Y=g["mean_y"], Time_mean=g["mean_x"])
+    g1.hyperparameters = g["hyp"].copy(); g1.nugget = 0.05
+    g1.get_prediction(svd_method=False)
+    assert_close(g1.Prediction[0], g["own_mean0"], 1e-9)
+    assert_close(g1.covariance_matrix[0], g["own_cov0"], 1e-9, 1e-12)
+
+
+def test_notebook_fits(cg):
+    """docs/notebook/1D_kernel_example_with_noise.ipynb cells 9 and 21."""
+    g = golden("notebook_with_noise")
+    gp = cg.gaussian_process(g["y"][0], g["x"][0], y_err=g["y_err"][0])
+    gp.find_hyperparameters(hyperparameter_guess=[0.5, 2], svd_method=False)
+    assert_close(gp.hyperparameters, g["printed_single"], 1e-4)
+    gn = cg.gaussian_process_nobject(g["y"], g["x"], y_err=g["y_err"])        # 2-D ndarray input
+    gn.find_hyperparameters(hyperparameter_guess=[0.5, 2], svd_method=False)
+    assert_close(gn.hyperparameters, g["printed_joint"], 1e-4)
+
+
+def test_build_pull_modes(cg):
+    g = golden("pulls_1d")
+    bp = cg.build_pull(list(g["y"]), list(g["x"]), g["hyp"], nugget=float(g["nugget"]), y_err=list(g["y_err"]))
+    bp.compute_pull(svd_method=False)
+    assert_close(bp.pull, g["pullA"], 1e-9, 1e-12); assert_close(bp.residual, g["residA"], 1e-9, 1e-12)
+    assert_close(np.array(bp.prediction), g["predA"], 1e-9, 1e-12)
+    assert_close([bp.pull_average, bp.pull_std], [g["pullA_avg"], g["pullA_std"]], 1e-9)
+    bd = cg.build_pull(list(g["yD"]), [g["xD"]] * 3, g["hyp"], nugget=float(g["nugget"]), y_err=list(g["y_err"][:3]))
+    bd.compute_pull(svd_method=False, substract_mean=True)
+    assert_close(bd.pull, g["pullD"], 1e-8, 1e-11)
+    r = golden("ragged_1d")
+    off = r["off"]
+    xs, ys, yes = (split(r[k], off) for k in ("x", "y", "y_err"))
+    bb = cg.build_pull(ys, xs, r["hyp"], nugget=0.05, y_err=yes, y_mean=r["mean_y"], x_axis_mean=r["mean_x"])
+    bb.compute_pull(svd_method=False)
+    assert_close(bb.pull, r["pullB"], 1e-8, 1e-11)
+    assert_close([bb.pull_average, bb.pull_std], [r["pullB_avg"], r["pullB_std"]], 1e-8)
+    bc = cg.build_pull(ys, xs, r["hyp"], nugget=0.05, y_err=yes, y_mean=r["mean_y"], x_axis_mean=r["mean_x"])
+    bc.compute_pull(diff=list(r["diff"]), svd_method=False)
+    assert_close(bc.pull, r["pullC"], 1e-8, 1e-11)
+
+
+def test_2d_objects(cg):
+    g = golden("batch_2d")
+    off = g["off"]
+    xs, ys, yes = split(g["x"], off), split(g["y"], off), split(g["y_err"], off)
+    gp = cg.gaussian_process_nobject(ys, xs, kernel="RBF2D", y_err=yes)
+    assert_close(gp.hyperparameters, g["init_rbf"], 1e-15)
+    gp.hyperparameters = g["hyp"].copy(); gp.nugget = float(g["nugget"])
+    gp.compute_log_likelihood(g["hyp"], svd_method=False)
+    assert_close(gp.log_likelihood[0], g["ll_sum"], 1e-9)
+    gp.get_prediction(new_binning=g["grid"], svd_method=False)
+    assert_close(np.array(gp.Prediction), g["mean"], 1e-9, 1e-12)
+    assert_close(gp.covariance_matrix[2], g["cov2"], 1e-9, 1e-11)
+    assert_close(gp.kernel_matrix[2], g["kmat2"], 1e-12, 1e-300)
+    bp = cg.build_pull(ys[2:], xs[2:], g["hyp"], nugget=float(g["nugget"]), y_err=yes[2:], kernel="RBF2D")
+    bp.compute_pull(svd_method=False)
+    assert_close(bp.pull, g["pull2"], 1e-9, 1e-12)
+
+
+def test_not_positive_definite_raises_linalgerror(cg):
+    x = np.array([0.0, 1.0, 1.0, 2.0]); y = np.array([0.1, 0.2, 0.3, 0.4])
+    gp = cg.gaussian_process(y, x)
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.compute_log_likelihood([1.0, 1.0], svd_method=False)

