@@ -27,7 +27,7 @@ def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    deps = [os.path.join(CSRC, s) for s in SOURCES + ["cgp_small64.cu"]] + HEADERS
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -36,10 +36,15 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    units = [(src, [], src.replace(".cu", ".o")) for src in SOURCES]
+    # the static N <= 64 kernel: one translation unit per (dim, task), built in parallel
+    units += [("cgp_small64.cu", ["-DCGP64_DIM=%d" % d, "-DCGP64_TASK=%d" % t], "cgp_small64_d%d_t%d.o" % (d, t))
+              for d in (1, 2) for t in (0, 1, 2)]
+    for src, defs, objname in units:
+        obj = os.path.join(CSRC, objname)
+        cmd = ([_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else [])
+               + ["-c", os.path.join(CSRC, src), "-o", obj])
+        procs.append((objname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()

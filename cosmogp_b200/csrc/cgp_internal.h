@@ -79,6 +79,14 @@ int large_residual(const double* y, const double* y0, int64_t n, int64_t n_pad, 
 int launch_small(Task task, int dim, int max_n, const SmallArgs& a, cudaStream_t stream);
 size_t small_smem_bytes(Task task, int dim, int nb);
 
+// N <= 64 fast path (cgp_small64.cu, one TU per dim/task)
+int launch_small64_d1_t0(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d1_t1(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d1_t2(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d2_t0(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d2_t1(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d2_t2(int nb, const SmallArgs& a, cudaStream_t stream);
+
 // FP64 ceiling probes (cgp_small.cu)
 int measure_fp64_peak(int kind, double* tflops);
 

@@ -613,6 +613,19 @@ size_t small_smem_bytes(Task task, int dim, int nb) {
 int launch_small(Task task, int dim, int max_n, const SmallArgs& a, cudaStream_t stream) {
   const int nbm = max_n < 1 ? 1 : (max_n + 7) / 8;
   if (nbm > 28) return (int)cudaErrorInvalidValue;
+  // N <= 64: the static one-warp-per-object kernel (CGP_SMALL_GENERIC=1 forces the generic one)
+  static int generic = -1;
+  if (generic < 0) { const char* e = getenv("CGP_SMALL_GENERIC"); generic = (e && atoi(e)) ? 1 : 0; }
+  if (!generic && nbm <= 8 && !a.amat && task != TASK_MATRICES) {
+    if (dim == 1) {
+      if (task == TASK_LL) return launch_small64_d1_t0(nbm, a, stream);
+      if (task == TASK_PREDICT) return launch_small64_d1_t1(nbm, a, stream);
+      return launch_small64_d1_t2(nbm, a, stream);
+    }
+    if (task == TASK_LL) return launch_small64_d2_t0(nbm, a, stream);
+    if (task == TASK_PREDICT) return launch_small64_d2_t1(nbm, a, stream);
+    return launch_small64_d2_t2(nbm, a, stream);
+  }
   return dim == 1 ? launch_task<1>(task, nbm, a, stream) : launch_task<2>(task, nbm, a, stream);
 }
 

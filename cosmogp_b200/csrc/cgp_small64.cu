@@ -1,0 +1,498 @@
+// gp64_kernel: the hot kernel for batches of small objects (N <= 64), one WARP per object,
+// the block count NB = ceil(N_max/8) a compile-time constant so that every tile loop is
+// straight-line code the scheduler can overlap (ncu, round 1: the generic kernel spent
+// 40 % of its issue slots waiting on dependent FP64 results and 12 % on loop/index code).
+//
+// Same algorithm and storage as cgp_small.cu (8x8 tiles in fragment order, left-looking block
+// Cholesky on DMMA, T_J = L_JJ^-1 on the diagonal slots), restructured in phases that are each
+// dense in independent FP64 work:
+//   K   all covariance tiles generated up front, 8 independent exp chains per lane in flight
+//   C   column J: every tile of the column accumulates its rank-8J update at once
+//       (2 (NB-J) independent DMMA chains), one parked-K subtraction, in-register diagonal
+//       factorisation, panel solve by DMMA
+//   S   LL: block forward substitution;  or  L^-1 by rows (NB-1 independent chains)
+//   P   predict: TWO blocks of 8 grid points per pass, all 4 NB cross-covariance fragments
+//       generated first, then 4 NB(NB+1)/2 DMMAs on 4 NB independent accumulators
+// Objects with fewer than NB blocks are padded with identity rows (exact, just wasteful);
+// per-object n masks the covariance entries.  Reference: see cgp_small.cu header.
+#include "cgp_internal.h"
+#include "cgp_math.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+namespace cgp {
+namespace {
+
+constexpr int TILE = 64;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr double LOG_2PI = 1.8378770664093454835606594728112;
+constexpr double LN2 = 0.693147180559945309417232;
+
+// (I << 4 | J) of the q-th tile of the lower block triangle, row by row (slot order)
+__constant__ unsigned char kTri[36] = {
+    0x00, 0x10, 0x11, 0x20, 0x21, 0x22, 0x30, 0x31, 0x32, 0x33, 0x40, 0x41, 0x42, 0x43, 0x44,
+    0x50, 0x51, 0x52, 0x53, 0x54, 0x55, 0x60, 0x61, 0x62, 0x63, 0x64, 0x65, 0x66,
+    0x70, 0x71, 0x72, 0x73, 0x74, 0x75, 0x76, 0x77};
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__host__ __device__ constexpr int slot(int i, int j) { return ((i * (i + 1)) >> 1) + j; }
+__device__ __forceinline__ int frag_off(int r, int c) { return ((r * 4 + (c & 3)) << 1) + (c >> 2); }
+
+struct Lane {
+  int g, t, fr, st0, st1, tr0, tr1;
+  __device__ explicit Lane(int lane) {
+    g = lane >> 2; t = lane & 3; fr = lane << 1;
+    st0 = frag_off(g, 2 * t); st1 = frag_off(g, 2 * t + 1);
+    tr0 = frag_off(t, g); tr1 = frag_off(4 + t, g);
+  }
+};
+__device__ __forceinline__ double2 ld_frag(const double* tiles, int s, const Lane& L) {
+  return *reinterpret_cast<const double2*>(tiles + s * TILE + L.fr);
+}
+__device__ __forceinline__ double red_t(double v) {
+  v += __shfl_xor_sync(FULL, v, 1); v += __shfl_xor_sync(FULL, v, 2); return v;
+}
+__device__ __forceinline__ double red_g(double v) {
+  v += __shfl_xor_sync(FULL, v, 4); v += __shfl_xor_sync(FULL, v, 8); v += __shfl_xor_sync(FULL, v, 16); return v;
+}
+
+template <int DIM>
+__device__ __forceinline__ double rbf_arg(const Cov& c, double ax, double ay, double bx, double by) {
+  const double dx = ax - bx;
+  if (DIM == 1) return dx * dx * c.h00;
+  const double dy = ay - by;
+  return fma(dy * c.h11, dy, fma(dx, c.h00, dy * c.h01) * dx);
+}
+
+// 8x8 Cholesky of a diagonal tile in accumulator layout + T = L^-1 by the same row operations
+// on an identity (see cgp_small.cu).  Rolled loop: 8 call sites share ~60 instructions each.
+__device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
+                                            double& t0, double& t1, double& pivprod, int& badk) {
+  t0 = (L.g == 2 * L.t) ? 1.0 : 0.0;
+  t1 = (L.g == 2 * L.t + 1) ? 1.0 : 0.0;
+  pivprod = 1.0; badk = 0;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const int kc = k >> 1;
+    const double ak = (k & 1) ? a1 : a0;
+    const double d = __shfl_sync(FULL, ak, k * 4 + kc);
+    if (!(d > 0.0) && badk == 0) badk = k + 1;
+    const double rinv = cgp_rsqrt(d);
+    pivprod *= d;
+    const double lg = __shfl_sync(FULL, ak, L.g * 4 + kc) * rinv;
+    const double lc0 = __shfl_sync(FULL, ak, (2 * L.t) * 4 + kc) * rinv;
+    const double lc1 = __shfl_sync(FULL, ak, (2 * L.t + 1) * 4 + kc) * rinv;
+    a0 = fma(-lg, lc0, a0); a1 = fma(-lg, lc1, a1);
+    const double tk0 = __shfl_sync(FULL, t0, k * 4 + L.t) * rinv;
+    const double tk1 = __shfl_sync(FULL, t1, k * 4 + L.t) * rinv;
+    if (L.g == k) { t0 = tk0; t1 = tk1; }
+    else if (L.g > k) { t0 = fma(-lg, tk0, t0); t1 = fma(-lg, tk1, t1); }
+  }
+}
+
+constexpr int n_vec64(int task) { return task == TASK_LL ? 1 : (task == TASK_PREDICT ? 3 : 6); }
+
+template <int DIM, int TASK, int NB>
+__global__ void __launch_bounds__(32)
+gp64_kernel(const SmallArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x;
+  const Lane L(lane);
+  const Cov cov = a.cov;
+  constexpr int LD = 8 * NB;
+  constexpr int NT = NB * (NB + 1) / 2;
+  double* tiles = smem;
+  double* px = tiles + NT * TILE;          // DIM * LD
+  double* noise = px + DIM * LD;
+  double* vr = noise + LD;                 // r (LL: becomes z)
+  double* vz = vr + LD;
+  double* va = vz + LD;
+  double* vd = va + LD;
+  double* v1 = vd + LD;
+  double* vu = v1 + LD;
+
+  const int split = (TASK == TASK_PREDICT) ? a.split : 1;
+  const int64_t n_work = a.n_obj * split;
+
+  for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int64_t oi = w / split;
+    const int part = (int)(w - oi * split);
+    const int64_t b = a.order ? a.order[oi] : oi;
+    const int64_t o0 = a.off[b];
+    const int n = (int)(a.off[b + 1] - o0);
+
+    // ---------------- stage
+    __syncwarp();
+    double rsum = 0.0;
+#pragma unroll
+    for (int i0 = 0; i0 < LD; i0 += 32) {
+      const int i = i0 + lane;
+      if (i < LD) {
+        const bool in = i < n;
+        if (DIM == 1) {
+          px[i] = in ? a.x[o0 + i] : 0.0;
+        } else {
+          px[i] = in ? a.x[2 * (o0 + i)] : 0.0;
+          px[LD + i] = in ? a.x[2 * (o0 + i) + 1] : 0.0;
+        }
+        const double ye = (in && a.yerr) ? a.yerr[o0 + i] : 0.0;
+        noise[i] = ye * ye + cov.noise_const;
+        const double r = in ? (a.y[o0 + i] - (a.y0 ? a.y0[o0 + i] : 0.0)) : 0.0;
+        vr[i] = r; rsum += r;
+      }
+    }
+    __syncwarp();
+    if (TASK == TASK_LOO) rsum = red_g(red_t(rsum));
+
+    // ---------------- phase K: covariance tiles, parked in their slots (accumulator values at
+    // fragment-order positions).  Two tiles per pass, unrolled twice: 8 exp chains per lane.
+#pragma unroll 2
+    for (int q = 0; q < NT; q += 2) {
+      double kv[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int qq = (q + u < NT) ? q + u : q;
+        const int ij = kTri[qq];
+        const int I = ij >> 4, J = ij & 15;
+        const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
+        const double xi = px[gi], yi = DIM == 2 ? px[LD + gi] : 0.0;
+        double e0 = 0.0, e1 = 0.0;
+        if (gi < n && cj < gi) e0 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj], DIM == 2 ? px[LD + cj] : 0.0));
+        if (gi < n && cj + 1 < gi) e1 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj + 1], DIM == 2 ? px[LD + cj + 1] : 0.0));
+        const double dg = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
+        kv[u][0] = (cj == gi) ? dg : cov.amp_auto * e0;
+        kv[u][1] = (cj + 1 == gi) ? dg : cov.amp_auto * e1;
+      }
+      double* p0 = tiles + q * TILE;
+      p0[L.st0] = kv[0][0]; p0[L.st1] = kv[0][1];
+      if (q + 1 < NT) { double* p1 = p0 + TILE; p1[L.st0] = kv[1][0]; p1[L.st1] = kv[1][1]; }
+    }
+    __syncwarp();
+
+    // ---------------- phase C: left-looking block Cholesky, column by column (static)
+    double lp_m = 1.0; int lp_e = 0; int bad = 0;
+#pragma unroll
+    for (int J = 0; J < NB; ++J) {
+      double s0[NB], s1[NB], u0[NB], u1[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) { s0[i] = 0.0; s1[i] = 0.0; u0[i] = 0.0; u1[i] = 0.0; }
+#pragma unroll
+      for (int P = 0; P < J; ++P) {
+        const double2 fb = ld_frag(tiles, slot(J, P), L);
+        dmma(s0[0], s1[0], fb.x, fb.x); dmma(u0[0], u1[0], fb.y, fb.y);
+#pragma unroll
+        for (int i = 1; i < NB - J; ++i) {
+          const double2 fa = ld_frag(tiles, slot(J + i, P), L);
+          dmma(s0[i], s1[i], fa.x, fb.x); dmma(u0[i], u1[i], fa.y, fb.y);
+        }
+      }
+      // C = K (parked) - update
+#pragma unroll
+      for (int i = 0; i < NB - J; ++i) {
+        const double* p = tiles + slot(J + i, J) * TILE;
+        s0[i] = p[L.st0] - (s0[i] + u0[i]);
+        s1[i] = p[L.st1] - (s1[i] + u1[i]);
+      }
+      __syncwarp();
+      {
+        double t0, t1, piv; int badk;
+        diag_factor(s0[0], s1[0], L, t0, t1, piv, badk);
+        double* p = tiles + slot(J, J) * TILE;
+        p[L.st0] = t0; p[L.st1] = t1;
+        if (TASK == TASK_LL) {
+          lp_m *= piv;
+          const int hi = __double2hiint(lp_m);
+          const int e = ((hi >> 20) & 0x7ff) - 1023;
+          lp_e += e;
+          lp_m = __hiloint2double(hi - (e << 20), __double2loint(lp_m));
+        }
+        if (badk && bad == 0) bad = 8 * J + badk;
+      }
+#pragma unroll
+      for (int i = 1; i < NB - J; ++i) {               // park C[I][J] to re-read it as an A fragment
+        double* p = tiles + slot(J + i, J) * TILE;
+        p[L.st0] = s0[i]; p[L.st1] = s1[i];
+      }
+      __syncwarp();
+      if (J + 1 < NB) {
+        const double2 ft = ld_frag(tiles, slot(J, J), L);
+#pragma unroll
+        for (int i = 1; i < NB - J; ++i) {             // L[I][J] = C[I][J] T_J^T
+          const double2 fc = ld_frag(tiles, slot(J + i, J), L);
+          s0[i] = 0.0; s1[i] = 0.0; u0[i] = 0.0; u1[i] = 0.0;
+          dmma(s0[i], s1[i], fc.x, ft.x); dmma(u0[i], u1[i], fc.y, ft.y);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 1; i < NB - J; ++i) {
+          double* p = tiles + slot(J + i, J) * TILE;
+          p[L.st0] = s0[i] + u0[i]; p[L.st1] = s1[i] + u1[i];
+        }
+        __syncwarp();
+      }
+    }
+
+    if (TASK == TASK_LL) {
+      // ---------------- z = L^-1 r by block forward substitution, quad = |z|^2
+      double quad = 0.0;
+#pragma unroll
+      for (int J = 0; J < NB; ++J) {
+        double p = 0.0, p2 = 0.0;
+#pragma unroll
+        for (int P = 0; P < J; ++P) {
+          const double2 f = ld_frag(tiles, slot(J, P), L);
+          p = fma(f.x, vr[8 * P + L.t], p); p2 = fma(f.y, vr[8 * P + 4 + L.t], p2);
+        }
+        const double wv = vr[8 * J + L.g] - red_t(p + p2);
+        const double2 f = ld_frag(tiles, slot(J, J), L);
+        double q = f.x * __shfl_sync(FULL, wv, L.t * 4) + f.y * __shfl_sync(FULL, wv, (4 + L.t) * 4);
+        q = red_t(q);
+        if (L.t == 0) { vr[8 * J + L.g] = q; quad = fma(q, q, quad); }
+        __syncwarp();
+      }
+      quad = red_g(red_t(quad));
+      if (lane == 0) {
+        a.info[b] = bad;
+        const double logdet = log(lp_m) + (double)lp_e * LN2;
+        a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+      }
+      continue;
+    }
+
+    // ---------------- L^-1 in place, row by row: L^-1[I][J] = -T_I sum_{P=J..I-1} L[I][P] L^-1[P][J]
+#pragma unroll
+    for (int I = 1; I < NB; ++I) {
+      double s0[NB], s1[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { s0[j] = 0.0; s1[j] = 0.0; }
+#pragma unroll
+      for (int P = 0; P < I; ++P) {
+        const double2 fa = ld_frag(tiles, slot(I, P), L);
+#pragma unroll
+        for (int J = 0; J <= P; ++J) {
+          const double* q = tiles + slot(P, J) * TILE;
+          dmma(s0[J], s1[J], fa.x, q[L.tr0]); dmma(s0[J], s1[J], fa.y, q[L.tr1]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int J = 0; J < I; ++J) { double* p = tiles + slot(I, J) * TILE; p[L.st0] = s0[J]; p[L.st1] = s1[J]; }
+      __syncwarp();
+      const double2 ft = ld_frag(tiles, slot(I, I), L);
+#pragma unroll
+      for (int J = 0; J < I; ++J) {
+        const double* q = tiles + slot(I, J) * TILE;
+        const double b0 = q[L.tr0], b1 = q[L.tr1];
+        s0[J] = 0.0; s1[J] = 0.0;
+        double e0 = 0.0, e1 = 0.0;
+        dmma(s0[J], s1[J], ft.x, b0); dmma(e0, e1, ft.y, b1);
+        s0[J] += e0; s1[J] += e1;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int J = 0; J < I; ++J) { double* p = tiles + slot(I, J) * TILE; p[L.st0] = -s0[J]; p[L.st1] = -s1[J]; }
+      __syncwarp();
+    }
+
+    // ---------------- z = L^-1 r (and L^-1 1), alpha = L^-T z, d = colnorm^2(L^-1), u = L^-T L^-1 1
+    const bool want_u = (TASK == TASK_LOO) && (a.loo_mode == 1);
+#pragma unroll
+    for (int I = 0; I < NB; ++I) {
+      double p = 0.0, p2 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int J = 0; J <= I; ++J) {
+        const double2 f = ld_frag(tiles, slot(I, J), L);
+        p = fma(f.x, vr[8 * J + L.t], p); p2 = fma(f.y, vr[8 * J + 4 + L.t], p2);
+        if (TASK == TASK_LOO) { p1 += f.x; p1 += f.y; }
+      }
+      p = red_t(p + p2);
+      if (L.t == 0) vz[8 * I + L.g] = p;
+      if (TASK == TASK_LOO) { p1 = red_t(p1); if (L.t == 0) v1[8 * I + L.g] = (8 * I + L.g < n) ? p1 : 0.0; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int J = 0; J < NB; ++J) {
+      double pa0 = 0.0, pa1 = 0.0, pd0 = 0.0, pd1 = 0.0, pu0 = 0.0, pu1 = 0.0;
+#pragma unroll
+      for (int I = J; I < NB; ++I) {
+        const double2 f = ld_frag(tiles, slot(I, J), L);
+        const double zi = vz[8 * I + L.g];
+        pa0 = fma(f.x, zi, pa0); pa1 = fma(f.y, zi, pa1);
+        if (TASK == TASK_LOO) {
+          const bool in = 8 * I + L.g < n;               // identity rows of the padding stay out
+          pd0 = in ? fma(f.x, f.x, pd0) : pd0; pd1 = in ? fma(f.y, f.y, pd1) : pd1;
+          const double ui = v1[8 * I + L.g];
+          pu0 = fma(f.x, ui, pu0); pu1 = fma(f.y, ui, pu1);
+        }
+      }
+      pa0 = red_g(pa0); pa1 = red_g(pa1);
+      if (L.g == 0) { va[8 * J + L.t] = pa0; va[8 * J + 4 + L.t] = pa1; }
+      if (TASK == TASK_LOO) {
+        pd0 = red_g(pd0); pd1 = red_g(pd1); pu0 = red_g(pu0); pu1 = red_g(pu1);
+        if (L.g == 0) {
+          vd[8 * J + L.t] = pd0; vd[8 * J + 4 + L.t] = pd1;
+          vu[8 * J + L.t] = pu0; vu[8 * J + 4 + L.t] = pu1;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && part == 0) a.info[b] = bad;
+
+    if (TASK == TASK_LOO) {
+      const double rho = cov.amp_cross / cov.amp_auto;
+      const double amp_star = cov.amp_auto + cov.nugget2;
+#pragma unroll
+      for (int i0 = 0; i0 < LD; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < n) {
+          const double d = vd[i], r = vr[i];
+          const double yv = a.y[o0 + i];
+          const double m = a.y0 ? a.y0[o0 + i] : 0.0;
+          const double ye = a.yerr ? a.yerr[o0 + i] : 0.0;
+          double pr = m + rho * (r - va[i] / d);
+          if (want_u) {
+            const double delta = (rsum - r) / (double)(n - 1);
+            pr += delta - delta * rho * (1.0 - vu[i] / d);
+          }
+          double pv = fabs(amp_star - rho * rho * (cov.amp_auto + noise[i] - 1.0 / d));
+          double res = pr - yv;
+          double pl = res / sqrt(ye * ye + pv + cov.nugget2);
+          if (bad) { pr = nan(""); pv = pr; res = pr; pl = pr; }
+          if (a.pred) a.pred[o0 + i] = pr;
+          if (a.pvar) a.pvar[o0 + i] = pv;
+          if (a.resid) a.resid[o0 + i] = res;
+          if (a.pull) a.pull[o0 + i] = pl;
+        }
+      }
+      continue;
+    }
+
+    if (TASK == TASK_PREDICT) {
+      // ---------------- two blocks of 8 grid points per pass
+      const int64_t g0 = a.goff ? a.goff[b] : 0;
+      const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
+      const int64_t out0 = a.goff ? g0 : b * a.m_shared;
+      const int64_t n_rb = (m_pts + 7) >> 3;
+      const double amp_star = cov.amp_auto + cov.nugget2;
+      for (int64_t rb = (int64_t)part * 2; rb < n_rb; rb += (int64_t)split * 2) {
+        int64_t mi[2]; bool live[2]; double gx[2], gy[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          mi[u] = 8 * (rb + u) + L.g;
+          live[u] = mi[u] < m_pts;
+          gx[u] = 0.0; gy[u] = 0.0;
+          if (live[u]) {
+            if (DIM == 1) gx[u] = a.xnew[g0 + mi[u]];
+            else { gx[u] = a.xnew[2 * (g0 + mi[u])]; gy[u] = a.xnew[2 * (g0 + mi[u]) + 1]; }
+          }
+        }
+        // cross-covariance fragments (no amplitude): 4 NB independent exps per lane
+        double h0[2][NB], h1[2][NB];
+        double pm[2] = {0.0, 0.0}, pm2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int P = 0; P < NB; ++P) {
+          const int c0 = 8 * P + L.t, c1 = c0 + 4;
+          const double x0 = px[c0], x1 = px[c1];
+          const double y0c = DIM == 2 ? px[LD + c0] : 0.0, y1c = DIM == 2 ? px[LD + c1] : 0.0;
+          const double al0 = va[c0], al1 = va[c1];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            double e0 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x0, y0c));
+            double e1 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x1, y1c));
+            e0 = (live[u] && c0 < n) ? e0 : 0.0;
+            e1 = (live[u] && c1 < n) ? e1 : 0.0;
+            h0[u][P] = e0; h1[u][P] = e1;
+            pm[u] = fma(e0, al0, pm[u]); pm2[u] = fma(e1, al1, pm2[u]);
+          }
+        }
+        double acc0[2][NB], acc1[2][NB];
+#pragma unroll
+        for (int J = 0; J < NB; ++J) { acc0[0][J] = 0.0; acc1[0][J] = 0.0; acc0[1][J] = 0.0; acc1[1][J] = 0.0; }
+#pragma unroll
+        for (int P = 0; P < NB; ++P) {
+#pragma unroll
+          for (int J = P; J < NB; ++J) {
+            const double2 fb = ld_frag(tiles, slot(J, P), L);
+            dmma(acc0[0][J], acc1[0][J], h0[0][P], fb.x); dmma(acc0[1][J], acc1[1][J], h0[1][P], fb.x);
+            dmma(acc0[0][J], acc1[0][J], h1[0][P], fb.y); dmma(acc0[1][J], acc1[1][J], h1[1][P], fb.y);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          double vv = 0.0, vv2 = 0.0;
+#pragma unroll
+          for (int J = 0; J < NB; ++J) { vv = fma(acc0[u][J], acc0[u][J], vv); vv2 = fma(acc1[u][J], acc1[u][J], vv2); }
+          const double pmt = red_t(pm[u] + pm2[u]);
+          vv = red_t(vv + vv2);
+          if (live[u] && L.t == 0) {
+            double mean = fma(cov.amp_cross, pmt, a.new_y0 ? a.new_y0[out0 + mi[u]] : 0.0);
+            double var = fma(-cov.amp_cross * cov.amp_cross, vv, amp_star);
+            if (bad) { mean = nan(""); var = mean; }
+            a.mean[out0 + mi[u]] = mean;
+            if (a.var) a.var[out0 + mi[u]] = var;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int DIM, int TASK, int NB>
+int launch64(const SmallArgs& a, cudaStream_t stream) {
+  auto kern = gp64_kernel<DIM, TASK, NB>;
+  const size_t smem = ((size_t)(NB * (NB + 1) / 2) * TILE + (size_t)(DIM + 1 + n_vec64(TASK)) * 8 * NB) * sizeof(double);
+  static int sm_count = 0;
+  static int per_sm = 0;
+  if (!sm_count) {
+    int dev; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (!per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
+  }
+  const int64_t n_work = a.n_obj * (TASK == TASK_PREDICT ? a.split : 1);
+  int64_t grid = (int64_t)sm_count * per_sm;
+  if (grid > n_work) grid = n_work;
+  if (grid < 1) return 0;
+  kern<<<(unsigned)grid, 32, smem, stream>>>(a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <int DIM, int TASK>
+int launch64_nb(int nb, const SmallArgs& a, cudaStream_t stream) {
+  switch (nb) {
+    case 1: return launch64<DIM, TASK, 1>(a, stream);
+    case 2: return launch64<DIM, TASK, 2>(a, stream);
+    case 3: return launch64<DIM, TASK, 3>(a, stream);
+    case 4: return launch64<DIM, TASK, 4>(a, stream);
+    case 5: return launch64<DIM, TASK, 5>(a, stream);
+    case 6: return launch64<DIM, TASK, 6>(a, stream);
+    case 7: return launch64<DIM, TASK, 7>(a, stream);
+    case 8: return launch64<DIM, TASK, 8>(a, stream);
+  }
+  return (int)cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+// One (DIM, TASK) pair per translation unit (build.py compiles this file six times with
+// -DCGP64_DIM / -DCGP64_TASK) so the 48 static instantiations build in parallel.
+#ifndef CGP64_DIM
+#error "compile with -DCGP64_DIM=1|2 -DCGP64_TASK=0|1|2"
+#endif
+#define CGP64_CAT2(a, b, c, d) a##b##c##d
+#define CGP64_CAT(a, b, c, d) CGP64_CAT2(a, b, c, d)
+int CGP64_CAT(launch_small64_d, CGP64_DIM, _t, CGP64_TASK)(int nb, const SmallArgs& a, cudaStream_t stream) {
+  return launch64_nb<CGP64_DIM, CGP64_TASK>(nb, a, stream);
+}
+
+}  // namespace cgp
