@@ -142,9 +142,11 @@ __device__ __forceinline__ void k_tile_minus(const Cov& cov, const double* px, c
     if (gi >= n && cj + 1 == gi) k1 = 1.0 - s1;
     return;
   }
-  double e0 = 0.0, e1 = 0.0;
-  if (gi < n && cj < gi) e0 = cov_e<DIM>(cov, px, ld, gi, cj);
-  if (gi < n && cj + 1 < gi) e1 = cov_e<DIM>(cov, px, ld, gi, cj + 1);
+  // branch-free (a conditional exp serialises the two chains); indices are always inside the staged arrays
+  double e0 = cov_e<DIM>(cov, px, ld, gi, cj);
+  double e1 = cov_e<DIM>(cov, px, ld, gi, cj + 1);
+  e0 = (gi < n && cj < gi) ? e0 : 0.0;
+  e1 = (gi < n && cj + 1 < gi) ? e1 : 0.0;
   k0 = fma(cov.amp_auto, e0, -s0);
   k1 = fma(cov.amp_auto, e1, -s1);
   const double dg = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;

@@ -94,7 +94,7 @@ __device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
   }
 }
 
-constexpr int n_vec64(int task) { return task == TASK_LL ? 1 : (task == TASK_PREDICT ? 3 : 6); }
+constexpr int n_vec64(int task) { return task == TASK_LOO ? 6 : 1; }
 
 template <int DIM, int TASK, int NB>
 __global__ void __launch_bounds__(32)
@@ -109,8 +109,9 @@ gp64_kernel(const SmallArgs a) {
   double* px = tiles + NT * TILE;          // DIM * LD
   double* noise = px + DIM * LD;
   double* vr = noise + LD;                 // r (LL: becomes z)
-  double* vz = vr + LD;
-  double* va = vz + LD;
+  // predict: z overwrites the (dead) noise vector and alpha overwrites r -> same footprint as LL
+  double* vz = (TASK == TASK_PREDICT) ? noise : vr + LD;
+  double* va = (TASK == TASK_PREDICT) ? vr : vz + LD;
   double* vd = va + LD;
   double* v1 = vd + LD;
   double* vu = v1 + LD;
@@ -150,26 +151,30 @@ gp64_kernel(const SmallArgs a) {
 
     // ---------------- phase K: covariance tiles, parked in their slots (accumulator values at
     // fragment-order positions).  Two tiles per pass, unrolled twice: 8 exp chains per lane.
-#pragma unroll 2
-    for (int q = 0; q < NT; q += 2) {
-      double kv[2][2];
+    constexpr int TPP = 4;                               // tiles per pass: 16 exp chains per lane in flight
+#pragma unroll 1
+    for (int q = 0; q < NT; q += TPP) {
+      double kv[TPP][2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < TPP; ++u) {
         const int qq = (q + u < NT) ? q + u : q;
         const int ij = kTri[qq];
         const int I = ij >> 4, J = ij & 15;
         const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
         const double xi = px[gi], yi = DIM == 2 ? px[LD + gi] : 0.0;
-        double e0 = 0.0, e1 = 0.0;
-        if (gi < n && cj < gi) e0 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj], DIM == 2 ? px[LD + cj] : 0.0));
-        if (gi < n && cj + 1 < gi) e1 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj + 1], DIM == 2 ? px[LD + cj + 1] : 0.0));
+        // branch-free: a conditional exp would serialise the chains (ncu r01c: 34 % of the time)
+        double e0 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj], DIM == 2 ? px[LD + cj] : 0.0));
+        double e1 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj + 1], DIM == 2 ? px[LD + cj + 1] : 0.0));
+        e0 = (gi < n && cj < gi) ? e0 : 0.0;
+        e1 = (gi < n && cj + 1 < gi) ? e1 : 0.0;
         const double dg = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
         kv[u][0] = (cj == gi) ? dg : cov.amp_auto * e0;
         kv[u][1] = (cj + 1 == gi) ? dg : cov.amp_auto * e1;
       }
-      double* p0 = tiles + q * TILE;
-      p0[L.st0] = kv[0][0]; p0[L.st1] = kv[0][1];
-      if (q + 1 < NT) { double* p1 = p0 + TILE; p1[L.st0] = kv[1][0]; p1[L.st1] = kv[1][1]; }
+#pragma unroll
+      for (int u = 0; u < TPP; ++u) {
+        if (q + u < NT) { double* p0 = tiles + (q + u) * TILE; p0[L.st0] = kv[u][0]; p0[L.st1] = kv[u][1]; }
+      }
     }
     __syncwarp();
 
@@ -379,12 +384,13 @@ gp64_kernel(const SmallArgs a) {
       const int64_t n_rb = (m_pts + 7) >> 3;
       const double amp_star = cov.amp_auto + cov.nugget2;
       for (int64_t rb = (int64_t)part * 2; rb < n_rb; rb += (int64_t)split * 2) {
-        int64_t mi[2]; bool live[2]; double gx[2], gy[2];
+        int64_t mi[2]; bool live[2]; double gx[2], gy[2], ny0[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           mi[u] = 8 * (rb + u) + L.g;
           live[u] = mi[u] < m_pts;
           gx[u] = 0.0; gy[u] = 0.0;
+          ny0[u] = (live[u] && a.new_y0) ? a.new_y0[out0 + mi[u]] : 0.0;   // issued early, consumed at the end
           if (live[u]) {
             if (DIM == 1) gx[u] = a.xnew[g0 + mi[u]];
             else { gx[u] = a.xnew[2 * (g0 + mi[u])]; gy[u] = a.xnew[2 * (g0 + mi[u]) + 1]; }
@@ -429,7 +435,7 @@ gp64_kernel(const SmallArgs a) {
           const double pmt = red_t(pm[u] + pm2[u]);
           vv = red_t(vv + vv2);
           if (live[u] && L.t == 0) {
-            double mean = fma(cov.amp_cross, pmt, a.new_y0 ? a.new_y0[out0 + mi[u]] : 0.0);
+            double mean = fma(cov.amp_cross, pmt, ny0[u]);
             double var = fma(-cov.amp_cross * cov.amp_cross, vv, amp_star);
             if (bad) { mean = nan(""); var = mean; }
             a.mean[out0 + mi[u]] = mean;
