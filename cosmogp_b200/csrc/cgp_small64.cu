@@ -94,11 +94,24 @@ __device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
   }
 }
 
+// Ring of work counters (one per launch in flight), zeroed in stream order before each launch.
+static unsigned long long* next_ticket(cudaStream_t stream) {
+  static unsigned long long* ring = nullptr;
+  static unsigned idx = 0;
+  constexpr unsigned RING = 256;
+  if (!ring && cudaMalloc((void**)&ring, RING * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+  unsigned long long* t = ring + (idx++ % RING);
+  if (cudaMemsetAsync(t, 0, sizeof(unsigned long long), stream) != cudaSuccess) return nullptr;
+  return t;
+}
+
 constexpr int n_vec64(int task) { return task == TASK_LOO ? 6 : 1; }
 
+// Registers are allocated per SM sub-partition (16 K each): 3 warps per partition need <= 168
+// registers per thread, hence the minimum-blocks bound (shared memory then allows 11 per SM).
 template <int DIM, int TASK, int NB>
-__global__ void __launch_bounds__(32)
-gp64_kernel(const SmallArgs a) {
+__global__ void __launch_bounds__(32, 12)
+gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
   const Lane L(lane);
@@ -119,7 +132,13 @@ gp64_kernel(const SmallArgs a) {
   const int split = (TASK == TASK_PREDICT) ? a.split : 1;
   const int64_t n_work = a.n_obj * split;
 
-  for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+  // Dynamic work distribution: 11 one-warp CTAs per SM land 3/3/3/2 on the four sub-partitions,
+  // so equal static shares would leave the 2-warp partition idle a quarter of the time.
+  int64_t w_next = blockIdx.x;
+  while (true) {
+    const int64_t w = __shfl_sync(FULL, w_next, 0);      // ticket drawn during the previous object
+    if (w >= n_work) break;
+    if (lane == 0) w_next = (int64_t)atomicAdd(ticket, 1ULL) + gridDim.x;
     const int64_t oi = w / split;
     const int part = (int)(w - oi * split);
     const int64_t b = a.order ? a.order[oi] : oi;
@@ -465,10 +484,14 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
     if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
   }
   const int64_t n_work = a.n_obj * (TASK == TASK_PREDICT ? a.split : 1);
-  int64_t grid = (int64_t)sm_count * per_sm;
+  static int cap = -1;                                    // experiment knob: CGP_GP64_PER_SM=<blocks per SM>
+  if (cap < 0) { const char* e = getenv("CGP_GP64_PER_SM"); cap = e ? atoi(e) : 0; }
+  int64_t grid = (int64_t)sm_count * ((cap > 0 && cap < per_sm) ? cap : per_sm);
   if (grid > n_work) grid = n_work;
   if (grid < 1) return 0;
-  kern<<<(unsigned)grid, 32, smem, stream>>>(a);
+  unsigned long long* ticket = next_ticket(stream);
+  if (!ticket) return (int)cudaErrorMemoryAllocation;
+  kern<<<(unsigned)grid, 32, smem, stream>>>(a, ticket);
   count_launch();
   return (int)cudaGetLastError();
 }
