@@ -187,3 +187,73 @@ class DeviceBatch:
             flat = self._down(t[:tot])
             out.append([flat[moff_h[i]:moff_h[i + 1]].reshape(sizes[i], sizes[i]) for i in range(self.n_obj)])
         return out[0], out[1], self._down(self._info[:self.n_obj])
+
+
+class StreamedEvaluator:
+    """LL + prediction of a host-resident batch with copies and kernels overlapped.
+
+    The batch is cut into chunks of objects; chunk k is uploaded on one of `n_streams` CUDA
+    streams while chunk k-1 computes and chunk k-2 downloads (PCIe is full duplex), so the
+    end-to-end time approaches max(copy, compute) instead of their sum.  Inputs and outputs
+    are pinned host arrays owned by this object; equal-length objects only (x, y, y0, y_err of
+    shape (B, N)), shared prediction grid."""
+
+    def __init__(self, n_obj, n_pts, m_grid, dim=1, n_chunks=8, n_streams=3, device=None):
+        _lib.require_device()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.B, self.N, self.M, self.dim = int(n_obj), int(n_pts), int(m_grid), int(dim)
+        self.bounds = np.linspace(0, self.B, min(n_chunks, max(self.B, 1)) + 1).astype(np.int64)
+        cmax = int(np.diff(self.bounds).max()) if self.B else 1
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
+        xs = (self.B, self.N, 2) if dim == 2 else (self.B, self.N)
+        pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        self.h = {"x": pin(*xs), "y": pin(self.B, self.N), "y0": pin(self.B, self.N), "y_err": pin(self.B, self.N),
+                  "new_y0": pin(self.B, self.M), "ll": pin(self.B), "mean": pin(self.B, self.M), "var": pin(self.B, self.M)}
+        self.h_info = torch.empty(self.B, dtype=torch.int32, pin_memory=True)
+        dev = lambda *shape: torch.empty(shape, dtype=torch.float64, device=self.device)
+        dxs = (cmax, self.N, 2) if dim == 2 else (cmax, self.N)
+        self.d = [{"x": dev(*dxs), "y": dev(cmax, self.N), "y0": dev(cmax, self.N), "y_err": dev(cmax, self.N),
+                   "new_y0": dev(cmax, self.M), "ll": dev(cmax), "mean": dev(cmax, self.M), "var": dev(cmax, self.M),
+                   "info": torch.empty(cmax, dtype=torch.int32, device=self.device),
+                   "off": (torch.arange(cmax + 1, dtype=torch.int64) * self.N).to(self.device)} for _ in range(n_streams)]
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def host(self, name):
+        """numpy view of a pinned staging array: fill inputs / read outputs in place."""
+        return self.h[name].numpy()
+
+    def run(self, hyp, nugget, grid, floor=0.0, flags=0):
+        """-> (ll_sum, ll (B,), mean (B,M), var (B,M), info (B,)) as numpy views of the pinned outputs."""
+        L = _lib.lib()
+        h = np.ascontiguousarray(np.asarray(hyp, dtype=np.float64).ravel())
+        g = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float64)).to(self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.h2d_bytes = self.d2h_bytes = 0
+        p = lambda t: t.data_ptr()
+        for k in range(len(self.bounds) - 1):
+            a, b = int(self.bounds[k]), int(self.bounds[k + 1])
+            nb = b - a
+            if nb == 0:
+                continue
+            st, d = self.streams[k % len(self.streams)], self.d[k % len(self.streams)]
+            with torch.cuda.stream(st):
+                for name in ("x", "y", "y0", "y_err", "new_y0"):
+                    d[name][:nb].copy_(self.h[name][a:b], non_blocking=True)
+                    self.h2d_bytes += self.h[name][a:b].numel() * 8
+                _lib.check(L.cgp_ll_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
+                                                p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), int(flags),
+                                                p(d["ll"]), p(d["info"]), st.cuda_stream), "cgp_ll_batched_dev")
+                _lib.check(L.cgp_predict_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
+                                                     p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), int(flags),
+                                                     p(g), None, self.M, p(d["new_y0"]), p(d["mean"]), p(d["var"]),
+                                                     p(d["info"]), st.cuda_stream), "cgp_predict_batched_dev")
+                self.h["ll"][a:b].copy_(d["ll"][:nb], non_blocking=True)
+                self.h["mean"][a:b].copy_(d["mean"][:nb], non_blocking=True)
+                self.h["var"][a:b].copy_(d["var"][:nb], non_blocking=True)
+                self.h_info[a:b].copy_(d["info"][:nb], non_blocking=True)
+                self.d2h_bytes += nb * (8 + 16 * self.M + 4)
+        for st in self.streams:
+            st.synchronize()
+        ll = self.h["ll"].numpy()
+        total = float(np.add.accumulate(ll)[-1]) if self.B else 0.0
+        return total, ll, self.h["mean"].numpy(), self.h["var"].numpy(), self.h_info.numpy()
