@@ -134,37 +134,54 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
 
   // Dynamic work distribution: 11 one-warp CTAs per SM land 3/3/3/2 on the four sub-partitions,
   // so equal static shares would leave the 2-warp partition idle a quarter of the time.
-  int64_t w_next = blockIdx.x;
-  while (true) {
-    const int64_t w = __shfl_sync(FULL, w_next, 0);      // ticket drawn during the previous object
+  // Software pipeline over objects: while object i is processed, the inputs of object i+1 are
+  // already in flight into registers (HBM latency ~700 cycles would otherwise be exposed per
+  // object) and the ticket for object i+2 is being drawn.
+  constexpr int NR = (LD + 31) / 32;                     // staged values per lane
+  struct Next { int64_t o0; int n; double x[NR], y2[NR], r[NR], ye[NR]; };
+  auto fetch = [&](int64_t w, Next& nx) {
+    nx.n = -1;
+    if (w >= n_work) return;
+    const int64_t oi = w / split;
+    const int64_t b = a.order ? a.order[oi] : oi;
+    nx.o0 = a.off[b];
+    nx.n = (int)(a.off[b + 1] - nx.o0);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int i = k * 32 + lane;
+      const bool in = i < nx.n;
+      if (DIM == 1) { nx.x[k] = in ? a.x[nx.o0 + i] : 0.0; nx.y2[k] = 0.0; }
+      else { nx.x[k] = in ? a.x[2 * (nx.o0 + i)] : 0.0; nx.y2[k] = in ? a.x[2 * (nx.o0 + i) + 1] : 0.0; }
+      nx.ye[k] = (in && a.yerr) ? a.yerr[nx.o0 + i] : 0.0;
+      nx.r[k] = in ? (a.y[nx.o0 + i] - (a.y0 ? a.y0[nx.o0 + i] : 0.0)) : 0.0;
+    }
+  };
+  int64_t w = blockIdx.x, w_nxt = (int64_t)blockIdx.x + gridDim.x, t_next = 0;
+  Next nx;
+  fetch(w, nx);
+  for (;; w = w_nxt, w_nxt = __shfl_sync(FULL, t_next, 0)) {
     if (w >= n_work) break;
-    if (lane == 0) w_next = (int64_t)atomicAdd(ticket, 1ULL) + gridDim.x;
+    if (lane == 0) t_next = (int64_t)atomicAdd(ticket, 1ULL) + 2 * (int64_t)gridDim.x;
     const int64_t oi = w / split;
     const int part = (int)(w - oi * split);
     const int64_t b = a.order ? a.order[oi] : oi;
-    const int64_t o0 = a.off[b];
-    const int n = (int)(a.off[b + 1] - o0);
+    const int64_t o0 = nx.o0;
+    const int n = nx.n;
 
-    // ---------------- stage
+    // ---------------- stage (from the prefetched registers), then start the next object's loads
     __syncwarp();
     double rsum = 0.0;
 #pragma unroll
-    for (int i0 = 0; i0 < LD; i0 += 32) {
-      const int i = i0 + lane;
+    for (int k = 0; k < NR; ++k) {
+      const int i = k * 32 + lane;
       if (i < LD) {
-        const bool in = i < n;
-        if (DIM == 1) {
-          px[i] = in ? a.x[o0 + i] : 0.0;
-        } else {
-          px[i] = in ? a.x[2 * (o0 + i)] : 0.0;
-          px[LD + i] = in ? a.x[2 * (o0 + i) + 1] : 0.0;
-        }
-        const double ye = (in && a.yerr) ? a.yerr[o0 + i] : 0.0;
-        noise[i] = ye * ye + cov.noise_const;
-        const double r = in ? (a.y[o0 + i] - (a.y0 ? a.y0[o0 + i] : 0.0)) : 0.0;
-        vr[i] = r; rsum += r;
+        px[i] = nx.x[k];
+        if (DIM == 2) px[LD + i] = nx.y2[k];
+        noise[i] = nx.ye[k] * nx.ye[k] + cov.noise_const;
+        vr[i] = nx.r[k]; rsum += nx.r[k];
       }
     }
+    fetch(w_nxt, nx);
     __syncwarp();
     if (TASK == TASK_LOO) rsum = red_g(red_t(rsum));
 
@@ -402,19 +419,30 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       const int64_t out0 = a.goff ? g0 : b * a.m_shared;
       const int64_t n_rb = (m_pts + 7) >> 3;
       const double amp_star = cov.amp_auto + cov.nugget2;
+      double pgx[2], pgy[2], pny0[2];
+      auto grid_fetch = [&](int64_t rb) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int64_t m = 8 * (rb + u) + L.g;
+          const bool lv = m < m_pts;
+          pgx[u] = 0.0; pgy[u] = 0.0;
+          if (lv) {
+            if (DIM == 1) pgx[u] = a.xnew[g0 + m];
+            else { pgx[u] = a.xnew[2 * (g0 + m)]; pgy[u] = a.xnew[2 * (g0 + m) + 1]; }
+          }
+          pny0[u] = (lv && a.new_y0) ? a.new_y0[out0 + m] : 0.0;
+        }
+      };
+      grid_fetch((int64_t)part * 2);
       for (int64_t rb = (int64_t)part * 2; rb < n_rb; rb += (int64_t)split * 2) {
         int64_t mi[2]; bool live[2]; double gx[2], gy[2], ny0[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           mi[u] = 8 * (rb + u) + L.g;
           live[u] = mi[u] < m_pts;
-          gx[u] = 0.0; gy[u] = 0.0;
-          ny0[u] = (live[u] && a.new_y0) ? a.new_y0[out0 + mi[u]] : 0.0;   // issued early, consumed at the end
-          if (live[u]) {
-            if (DIM == 1) gx[u] = a.xnew[g0 + mi[u]];
-            else { gx[u] = a.xnew[2 * (g0 + mi[u])]; gy[u] = a.xnew[2 * (g0 + mi[u]) + 1]; }
-          }
+          gx[u] = pgx[u]; gy[u] = pgy[u]; ny0[u] = pny0[u];
         }
+        grid_fetch(rb + (int64_t)split * 2);               // next pair's coordinates, behind this pair's math
         // cross-covariance fragments (no amplitude): 4 NB independent exps per lane
         double h0[2][NB], h1[2][NB];
         double pm[2] = {0.0, 0.0}, pm2[2] = {0.0, 0.0};
