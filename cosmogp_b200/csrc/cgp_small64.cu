@@ -20,6 +20,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace cgp {
 namespace {
@@ -494,8 +495,208 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Compact log-likelihood kernel.  The likelihood needs row J of L only until z_J is solved,
+// so rows are RETIRED as the factorisation advances and their shared-memory slots are reused
+// by later columns: at most (NB-J)(J+1) tiles are live (20 instead of 36 at NB = 8), the
+// covariance column is generated in registers right when it is consumed (no parking), and
+// 16 warps (4 per sub-partition, balanced) fit on an SM instead of 11.
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) { f(std::integral_constant<int, B>{}); static_for<B + 1, E>(f); }
+}
+
+// kPhys[NB-1][I][P]: shared-memory slot of tile (I,P) when rows are retired after their solve
+// (first-free allocation, generated by the simulation in the comment of gp64_ll_kernel)
+constexpr int kPhys[8][8][8] = {
+    {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}},
+    {{0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}},
+    {{0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0}, {2, 3, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}},
+    {{0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0}, {2, 4, 0, 0, 0, 0, 0, 0}, {3, 5, 1, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}},
+    {{0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0}, {2, 5, 0, 0, 0, 0, 0, 0}, {3, 6, 1, 0, 0, 0, 0, 0}, {4, 7, 8, 2, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}},
+    {{0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0}, {2, 6, 0, 0, 0, 0, 0, 0}, {3, 7, 1, 0, 0, 0, 0, 0}, {4, 8, 10, 2, 0, 0, 0, 0}, {5, 9, 11, 6, 1, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}},
+    {{0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0}, {2, 7, 0, 0, 0, 0, 0, 0}, {3, 8, 1, 0, 0, 0, 0, 0}, {4, 9, 12, 2, 0, 0, 0, 0}, {5, 10, 13, 7, 1, 0, 0, 0}, {6, 11, 14, 15, 3, 2, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}},
+    {{0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0}, {2, 8, 0, 0, 0, 0, 0, 0}, {3, 9, 1, 0, 0, 0, 0, 0}, {4, 10, 14, 2, 0, 0, 0, 0}, {5, 11, 15, 8, 1, 0, 0, 0}, {6, 12, 16, 18, 3, 2, 0, 0}, {7, 13, 17, 19, 9, 4, 1, 0}}};
+constexpr int kPhysSlots[8] = {1, 2, 4, 6, 9, 12, 16, 20};
+
+template <int DIM, int NB>
+__global__ void __launch_bounds__(32, 16)
+gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x;
+  const Lane L(lane);
+  const Cov cov = a.cov;
+  constexpr int LD = 8 * NB;
+  constexpr int NSLOT = kPhysSlots[NB - 1];
+  double* tiles = smem;
+  double* px = tiles + NSLOT * TILE;
+  double* noise = px + DIM * LD;
+  double* vr = noise + LD;
+  const int64_t n_work = a.n_obj;
+
+  constexpr int NR = (LD + 31) / 32;
+  struct Next { int64_t b; int n; double x[NR], y2[NR], r[NR], ye[NR]; };
+  auto fetch = [&](int64_t w, Next& nx) {
+    nx.n = -1; nx.b = 0;
+    if (w >= n_work) return;
+    nx.b = a.order ? a.order[w] : w;
+    const int64_t o0 = a.off[nx.b];
+    nx.n = (int)(a.off[nx.b + 1] - o0);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int i = k * 32 + lane;
+      const bool in = i < nx.n;
+      if (DIM == 1) { nx.x[k] = in ? a.x[o0 + i] : 0.0; nx.y2[k] = 0.0; }
+      else { nx.x[k] = in ? a.x[2 * (o0 + i)] : 0.0; nx.y2[k] = in ? a.x[2 * (o0 + i) + 1] : 0.0; }
+      nx.ye[k] = (in && a.yerr) ? a.yerr[o0 + i] : 0.0;
+      nx.r[k] = in ? (a.y[o0 + i] - (a.y0 ? a.y0[o0 + i] : 0.0)) : 0.0;
+    }
+  };
+  int64_t w = blockIdx.x, w_nxt = (int64_t)blockIdx.x + gridDim.x, t_next = 0;
+  Next nx;
+  fetch(w, nx);
+  for (;; w = w_nxt, w_nxt = __shfl_sync(FULL, t_next, 0)) {
+    if (w >= n_work) break;
+    if (lane == 0) t_next = (int64_t)atomicAdd(ticket, 1ULL) + 2 * (int64_t)gridDim.x;
+    const int64_t b = nx.b;
+    const int n = nx.n;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int i = k * 32 + lane;
+      if (i < LD) {
+        px[i] = nx.x[k];
+        if (DIM == 2) px[LD + i] = nx.y2[k];
+        noise[i] = nx.ye[k] * nx.ye[k] + cov.noise_const;
+        vr[i] = nx.r[k];
+      }
+    }
+    fetch(w_nxt, nx);
+    __syncwarp();
+
+    double lp_m = 1.0, quad = 0.0; int lp_e = 0; int bad = 0;
+    static_for<0, NB>([&](auto Jc) {
+      constexpr int J = decltype(Jc)::value;
+      constexpr int NTJ = NB - J;
+      // covariance column J, straight into accumulator layout (2 NTJ independent exp chains)
+      double k0[NTJ], k1[NTJ];
+      static_for<0, NTJ>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const int gi = 8 * (J + i) + L.g, cj = 8 * J + 2 * L.t;
+        const double xi = px[gi], yi = DIM == 2 ? px[LD + gi] : 0.0;
+        double e0 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj], DIM == 2 ? px[LD + cj] : 0.0));
+        double e1 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj + 1], DIM == 2 ? px[LD + cj + 1] : 0.0));
+        e0 = (gi < n && cj < gi) ? e0 : 0.0;
+        e1 = (gi < n && cj + 1 < gi) ? e1 : 0.0;
+        const double dg = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
+        k0[i] = (i == 0 && cj == gi) ? dg : cov.amp_auto * e0;
+        k1[i] = (i == 0 && cj + 1 == gi) ? dg : cov.amp_auto * e1;
+      });
+      // rank-8J update of the whole column: 2 NTJ independent DMMA chains
+      double s0[NTJ], s1[NTJ], u0[NTJ], u1[NTJ];
+      static_for<0, NTJ>([&](auto ic) { constexpr int i = decltype(ic)::value; s0[i] = 0.0; s1[i] = 0.0; u0[i] = 0.0; u1[i] = 0.0; });
+      static_for<0, J>([&](auto Pc) {
+        constexpr int P = decltype(Pc)::value;
+        const double2 fb = ld_frag(tiles, kPhys[NB - 1][J][P], L);
+        dmma(s0[0], s1[0], fb.x, fb.x); dmma(u0[0], u1[0], fb.y, fb.y);
+        static_for<1, NTJ>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          const double2 fa = ld_frag(tiles, kPhys[NB - 1][J + i][P], L);
+          dmma(s0[i], s1[i], fa.x, fb.x); dmma(u0[i], u1[i], fa.y, fb.y);
+        });
+      });
+      static_for<0, NTJ>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        s0[i] = k0[i] - (s0[i] + u0[i]); s1[i] = k1[i] - (s1[i] + u1[i]);
+      });
+      {
+        double t0, t1, piv; int badk;
+        diag_factor(s0[0], s1[0], L, t0, t1, piv, badk);
+        double* p = tiles + kPhys[NB - 1][J][J] * TILE;
+        p[L.st0] = t0; p[L.st1] = t1;
+        lp_m *= piv;
+        const int hi = __double2hiint(lp_m);
+        const int e = ((hi >> 20) & 0x7ff) - 1023;
+        lp_e += e;
+        lp_m = __hiloint2double(hi - (e << 20), __double2loint(lp_m));
+        if (badk && bad == 0) bad = 8 * J + badk;
+      }
+      static_for<1, NTJ>([&](auto ic) {                 // park C[I][J] to re-read it as an A fragment
+        constexpr int i = decltype(ic)::value;
+        double* p = tiles + kPhys[NB - 1][J + i][J] * TILE;
+        p[L.st0] = s0[i]; p[L.st1] = s1[i];
+      });
+      __syncwarp();
+      const double2 ft = ld_frag(tiles, kPhys[NB - 1][J][J], L);
+      if constexpr (NTJ > 1) {
+        static_for<1, NTJ>([&](auto ic) {               // L[I][J] = C[I][J] T_J^T
+          constexpr int i = decltype(ic)::value;
+          const double2 fc = ld_frag(tiles, kPhys[NB - 1][J + i][J], L);
+          s0[i] = 0.0; s1[i] = 0.0; u0[i] = 0.0; u1[i] = 0.0;
+          dmma(s0[i], s1[i], fc.x, ft.x); dmma(u0[i], u1[i], fc.y, ft.y);
+        });
+        __syncwarp();
+        static_for<1, NTJ>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          double* p = tiles + kPhys[NB - 1][J + i][J] * TILE;
+          p[L.st0] = s0[i] + u0[i]; p[L.st1] = s1[i] + u1[i];
+        });
+      }
+      // z_J = T_J (r_J - sum_{P<J} L[J][P] z_P); afterwards row J is dead and its slots are reused
+      double pz = 0.0, pz2 = 0.0;
+      static_for<0, J>([&](auto Pc) {
+        constexpr int P = decltype(Pc)::value;
+        const double2 f = ld_frag(tiles, kPhys[NB - 1][J][P], L);
+        pz = fma(f.x, vr[8 * P + L.t], pz); pz2 = fma(f.y, vr[8 * P + 4 + L.t], pz2);
+      });
+      const double wv = vr[8 * J + L.g] - red_t(pz + pz2);
+      double q = ft.x * __shfl_sync(FULL, wv, L.t * 4) + ft.y * __shfl_sync(FULL, wv, (4 + L.t) * 4);
+      q = red_t(q);
+      if (L.t == 0) { vr[8 * J + L.g] = q; quad = fma(q, q, quad); }
+      __syncwarp();
+    });
+    quad = red_g(red_t(quad));
+    if (lane == 0) {
+      a.info[b] = bad;
+      const double logdet = log(lp_m) + (double)lp_e * LN2;
+      a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+    }
+  }
+}
+
+
+template <int DIM, int NB>
+int launch64_ll(const SmallArgs& a, cudaStream_t stream) {
+  auto kern = gp64_ll_kernel<DIM, NB>;
+  const size_t smem = ((size_t)kPhysSlots[NB - 1] * TILE + (size_t)(DIM + 2) * 8 * NB) * sizeof(double);
+  static int sm_count = 0, per_sm = 0;
+  if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  if (!per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
+    if (per_sm > 16) per_sm = 16;                        // 4 warps per sub-partition
+  }
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("CGP_GP64_PER_SM"); cap = e ? atoi(e) : 0; }
+  int64_t grid = (int64_t)sm_count * ((cap > 0 && cap < per_sm) ? cap : per_sm);
+  if (grid > a.n_obj) grid = a.n_obj;
+  if (grid < 1) return 0;
+  unsigned long long* ticket = next_ticket(stream);
+  if (!ticket) return (int)cudaErrorMemoryAllocation;
+  kern<<<(unsigned)grid, 32, smem, stream>>>(a, ticket);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 template <int DIM, int TASK, int NB>
 int launch64(const SmallArgs& a, cudaStream_t stream) {
+  static int compact = -1;                                // CGP_LL_COMPACT=0 falls back to the 36-slot kernel
+  if (compact < 0) { const char* e = getenv("CGP_LL_COMPACT"); compact = (e && !atoi(e)) ? 0 : 1; }
+  if (TASK == TASK_LL && compact) return launch64_ll<DIM, NB>(a, stream);
   auto kern = gp64_kernel<DIM, TASK, NB>;
   const size_t smem = ((size_t)(NB * (NB + 1) / 2) * TILE + (size_t)(DIM + 1 + n_vec64(TASK)) * 8 * NB) * sizeof(double);
   static int sm_count = 0;
