@@ -117,6 +117,30 @@ class DeviceBatch:
         total = float(np.add.accumulate(ll_h)[-1]) if self.n_obj else 0.0   # left-to-right, like :205-213
         return total, ll_h, info_h
 
+    def ll_objhyp(self, hyp_rows, idx, nugget_rows=None, nugget=0.0, floor=0.0, flags=0):
+        """Log-likelihood of the objects `idx` (int array), object idx[k] using its own
+        hyperparameters hyp_rows[k] (and nugget_rows[k]).  -> (ll (k,), info (k,)) host arrays."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        k, nh = len(idx), (2 if self.dim == 1 else 4)
+        if k == 0:
+            return np.zeros(0), np.zeros(0, dtype=np.int32)
+        full = np.zeros((self.n_obj, nh)); full[idx] = np.asarray(hyp_rows, dtype=np.float64).reshape(k, nh)
+        hd = self._up(full)
+        nd = None
+        if nugget_rows is not None:
+            fn = np.zeros(self.n_obj); fn[idx] = np.asarray(nugget_rows, dtype=np.float64)
+            nd = self._up(fn)
+        order = self._up(idx.astype(np.int32)) if k < self.n_obj or not np.array_equal(idx, np.arange(k)) else None
+        ll = torch.empty(max(self.n_obj, 1), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_ll_objhyp_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                              self._p(self.y), self._p(self.y0), self._p(self.y_err), self._p(hd),
+                                              self._p(nd), float(nugget), float(floor), int(flags), self._p(order), k,
+                                              self._p(ll), self._p(self._info), self._stream())
+        _lib.check(rc, "cgp_ll_objhyp_dev")
+        ll_h = self._down(ll[:self.n_obj]); info_h = self._down(self._info[:self.n_obj])
+        return ll_h[idx], info_h[idx]
+
     def predict_dev(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0):
         h = self._hyp(hyp)
         m = 0 if goff is not None else int(grid.shape[0])

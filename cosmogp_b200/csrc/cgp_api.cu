@@ -34,21 +34,8 @@ static int cuda_fail(int e, const char* where) {
 // hyp -> Cov  (cosmogp/kernel.py:71-75 for 1D, :127-151 for 2D)
 static int make_cov(int dim, const double* hyp, double nugget, double floor, unsigned flags, Cov* c) {
   if (!hyp) return fail(CGP_ERR_ARG, "hyp is NULL");
-  const double s2 = hyp[0] * hyp[0];
-  if (dim == 1) {
-    c->amp_auto = s2; c->amp_cross = s2;
-    c->h00 = -0.5 / (hyp[1] * hyp[1]); c->h01 = 0.0; c->h11 = 0.0;
-  } else if (dim == 2) {
-    const double lx2 = hyp[1] * hyp[1], ly2 = hyp[2] * hyp[2], lxy = hyp[3];
-    const double sc = 1.0 / (lx2 * ly2 - lxy * lxy);        // NaN/inf metric propagates, like scipy
-    c->h00 = -0.5 * (ly2 * sc); c->h01 = lxy * sc; c->h11 = -0.5 * (lx2 * sc);
-    c->amp_cross = s2;
-    c->amp_auto = (flags & CGP_AMP_ON_AUTOCOV) ? s2 : 1.0;  // HEAD drops sigma^2 (kernel.py:146-148)
-  } else {
-    return fail(CGP_ERR_ARG, "dim must be 1 or 2, got %d", dim);
-  }
-  c->noise_const = floor * floor + nugget * nugget;
-  c->nugget2 = nugget * nugget;
+  if (dim != 1 && dim != 2) return fail(CGP_ERR_ARG, "dim must be 1 or 2, got %d", dim);
+  *c = cov_from_hyp(dim, hyp, nugget, floor, flags);
   return 0;
 }
 
@@ -182,6 +169,25 @@ int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
   if (!hc.sync()) return cuda_fail((int)hc.err, "cgp_ll_batched_host");
   if (ll_sum) { double s = 0.0; for (int64_t i = 0; i < n_obj; ++i) s += ll_obj[i]; *ll_sum = s; }
   return count_bad(info, n_obj);
+}
+
+// One likelihood evaluation with PER-OBJECT hyperparameters (device arrays): the building block of
+// lock-step per-object fits (the notebook loop `for i: gaussian_process(y[i], x[i]).find_hyperparameters()`).
+int cgp_ll_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                      const double* x, const double* y, const double* y0, const double* y_err,
+                      const double* hyp_obj, const double* nugget_obj, double nugget, double floor, unsigned flags,
+                      const int* order, int64_t n_active, double* ll_obj, int* info, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !hyp_obj || !ll_obj || !info)))
+    return fail(CGP_ERR_ARG, "cgp_ll_objhyp_dev: NULL argument");
+  if (dim != 1 && dim != 2) return fail(CGP_ERR_ARG, "dim must be 1 or 2, got %d", dim);
+  if (max_n <= 0) return fail(CGP_ERR_ARG, "cgp_ll_objhyp_dev: max_n is required");
+  SmallArgs a; memset(&a, 0, sizeof a);
+  a.n_obj = order ? n_active : n_obj; a.off = off; a.order = order;
+  a.x = x; a.y = y; a.y0 = y0; a.yerr = y_err; a.ll = ll_obj; a.info = info;
+  a.hyp_obj = hyp_obj; a.n_hyp = dim == 1 ? 2 : 4; a.nugget_obj = nugget_obj; a.nugget_shared = nugget;
+  a.floor_shared = floor; a.flags = flags;
+  a.cov = Cov();
+  return run_small(TASK_LL, dim, max_n, a, (cudaStream_t)stream, "cgp_ll_objhyp_dev");
 }
 
 // ------------------------------------------------------------------------------------ predict

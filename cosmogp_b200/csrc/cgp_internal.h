@@ -17,6 +17,28 @@ struct Cov {
   double nugget2;      // nugget^2: K(x*,x*) carries it but not y_err^2 (Gaussian_process.py:357)
 };
 
+#define CGP_FLAG_AMP_ON_AUTOCOV 1u
+
+// hyp -> Cov (cosmogp/kernel.py:71-75 for 1D, :127-151 for 2D); shared by the host API and by the
+// kernels when every object carries its own hyperparameters.  A singular / NaN metric propagates.
+__host__ __device__ inline Cov cov_from_hyp(int dim, const double* hyp, double nugget, double floor, unsigned flags) {
+  Cov c;
+  const double s2 = hyp[0] * hyp[0];
+  c.amp_cross = s2;
+  if (dim == 1) {
+    c.amp_auto = s2;
+    c.h00 = -0.5 / (hyp[1] * hyp[1]); c.h01 = 0.0; c.h11 = 0.0;
+  } else {
+    const double lx2 = hyp[1] * hyp[1], ly2 = hyp[2] * hyp[2], lxy = hyp[3];
+    const double sc = 1.0 / (lx2 * ly2 - lxy * lxy);
+    c.h00 = -0.5 * (ly2 * sc); c.h01 = lxy * sc; c.h11 = -0.5 * (lx2 * sc);
+    c.amp_auto = (flags & CGP_FLAG_AMP_ON_AUTOCOV) ? s2 : 1.0;   // HEAD drops sigma^2 (kernel.py:146-148)
+  }
+  c.noise_const = floor * floor + nugget * nugget;
+  c.nugget2 = nugget * nugget;
+  return c;
+}
+
 enum Task { TASK_LL = 0, TASK_PREDICT = 1, TASK_LOO = 2, TASK_MATRICES = 3 };
 
 struct SmallArgs {
@@ -28,6 +50,9 @@ struct SmallArgs {
   const double* y0;        // may be null
   const double* yerr;      // may be null
   Cov cov;
+  // per-object hyperparameters (lock-step per-object fits): when hyp_obj != null object b uses
+  // hyp_obj[b*n_hyp ..] and nugget_obj[b] (or nugget_shared) instead of `cov`
+  const double* hyp_obj; int n_hyp; const double* nugget_obj; double nugget_shared; double floor_shared; unsigned flags;
   int* info;               // [n_obj]
   // TASK_LL
   double* ll;              // [n_obj]

@@ -160,7 +160,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Lane L(lane);
-  const Cov cov = a.cov;
+  Cov cov = a.cov;
   constexpr int NT = WARPS * 32;
   constexpr int KMAX = (NB_MAX - 1 + WARPS - 1) / WARPS;   // L^-1 row: tiles per warp
 
@@ -188,6 +188,8 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
     const int n = (int)(a.off[b + 1] - o0);
     const int nb = (n + 7) >> 3;
     const double* amat = a.amat ? a.amat + a.aoff[b] : nullptr;
+    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + b * a.n_hyp, a.nugget_obj ? a.nugget_obj[b] : a.nugget_shared,
+                                      a.floor_shared, a.flags);
 
     // ---------------- stage the object
     cta_sync<WARPS>();                                    // previous object fully consumed

@@ -116,7 +116,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
   const Lane L(lane);
-  const Cov cov = a.cov;
+  Cov cov = a.cov;
   constexpr int LD = 8 * NB;
   constexpr int NT = NB * (NB + 1) / 2;
   double* tiles = smem;
@@ -168,6 +168,8 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     const int64_t b = a.order ? a.order[oi] : oi;
     const int64_t o0 = nx.o0;
     const int n = nx.n;
+    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + b * a.n_hyp, a.nugget_obj ? a.nugget_obj[b] : a.nugget_shared,
+                                      a.floor_shared, a.flags);
 
     // ---------------- stage (from the prefetched registers), then start the next object's loads
     __syncwarp();
@@ -526,7 +528,7 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
   const Lane L(lane);
-  const Cov cov = a.cov;
+  Cov cov = a.cov;
   constexpr int LD = 8 * NB;
   constexpr int NSLOT = kPhysSlots[NB - 1];
   double* tiles = smem;
@@ -561,6 +563,8 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     if (lane == 0) t_next = (int64_t)atomicAdd(ticket, 1ULL) + 2 * (int64_t)gridDim.x;
     const int64_t b = nx.b;
     const int n = nx.n;
+    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + b * a.n_hyp, a.nugget_obj ? a.nugget_obj[b] : a.nugget_shared,
+                                      a.floor_shared, a.flags);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < NR; ++k) {

@@ -153,6 +153,35 @@ class Gaussian_process:
         if self.fit_nugget:
             self.nugget = np.sqrt(hyperparameters[-1] ** 2)
 
+    def find_hyperparameters_per_object(self, hyperparameter_guess=None, nugget=False, svd_method=True):
+        """One maximum-likelihood fit PER OBJECT -- the batched form of the reference's loop
+        `for i: gp = gaussian_process(y[i], Time[i], ...); gp.find_hyperparameters(guess)`
+        (docs/notebook/1D_kernel_example_with_noise.ipynb cell 13).  scipy's Nelder-Mead is replayed
+        in lock step for all objects (cosmogp_b200.fit); every evaluation is one device launch.
+        Sets `hyperparameters_per_object` (N_sn, n_hyp), `nugget_per_object` (N_sn,) and
+        `log_likelihood_per_object`; an object whose covariance is not positive definite at a trial
+        point gets +inf there (the reference would abort with LinAlgError)."""
+        from .fit import nelder_mead_lockstep
+        guess = np.asarray(self.hyperparameters if hyperparameter_guess is None else hyperparameter_guess, dtype=float)
+        assert len(self.hyperparameters) == len(guess), 'should be same len'
+        nh = len(guess)
+        start = list(guess) + ([1.] if nugget else [])
+        x0 = np.tile(np.asarray(start, dtype=float), (self.N_sn, 1))
+        base_nugget = float(self.nugget)
+
+        def fun(X, idx):
+            ll, info = self.batch.ll_objhyp(X[:, :nh], idx, nugget_rows=X[:, nh] if nugget else None,
+                                            nugget=base_nugget, flags=self.flags)
+            f = -ll
+            f[(info != 0) | ~np.isfinite(f)] = np.inf
+            return f
+
+        x, fval, its, calls = nelder_mead_lockstep(fun, x0)
+        self.hyperparameters_per_object = np.sqrt(x[:, :nh] ** 2)              # abs, like :249-250
+        self.nugget_per_object = np.sqrt(x[:, nh] ** 2) if nugget else np.full(self.N_sn, base_nugget)
+        self.log_likelihood_per_object = -fval
+        self.fit_iterations, self.fit_evaluations = its, calls
+
     # ------------------------------------------------------------------ matrices
     def compute_kernel_matrix(self):
         """kernel_matrix[sn] = K(Time[sn]) with nugget and y_err (:256-267), on access."""

@@ -74,6 +74,17 @@ int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
                         const double* hyp, double nugget, double floor, unsigned flags,
                         double* ll_obj, int* info, double* ll_sum);
 
+/* ---- per-object fits: one likelihood evaluation where object b uses its OWN hyperparameters
+ *      hyp_obj[b*nh .. b*nh+nh) (nh = 2 or 4) and nugget_obj[b] (NULL -> the shared `nugget`).
+ *      order (device, may be NULL) restricts the evaluation to n_active object ids; ll_obj / info
+ *      are indexed by object id.  This is the batched form of the reference's per-object loop
+ *      `gaussian_process(y[i], x[i]).find_hyperparameters()` (docs/notebook/1D_kernel_example_with_noise.ipynb
+ *      cell 13): scipy's Nelder-Mead runs in lock step over all objects on the host. */
+int cgp_ll_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                      const double* x, const double* y, const double* y0, const double* y_err,
+                      const double* hyp_obj, const double* nugget_obj, double nugget, double floor, unsigned flags,
+                      const int* order, int64_t n_active, double* ll_obj, int* info, void* stream);
+
 /* ---- prediction: replaces Gaussian_process.get_prediction + get_covariance_matrix
  *      (cosmogp/Gaussian_process.py:270-361).
  *      Grid: if goff == NULL the m_shared points of xnew are shared by all objects
