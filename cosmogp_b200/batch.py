@@ -156,6 +156,35 @@ class DeviceBatch:
         _lib.check(rc, "cgp_predict_batched_dev")
         return mean[:nout], (var[:nout] if want_var else None), self._info[:self.n_obj]
 
+    def factor_dev(self, hyp, nugget=0.0, floor=0.0, flags=0):
+        """Factorise every object once (objects of <= 64 points): returns an opaque device workspace
+        holding inv(L) and alpha, reusable by predict_factored_dev for any number of grids."""
+        assert 0 < self.max_n <= 64, "factor_dev handles objects of 1..64 points"
+        h = self._hyp(hyp)
+        stride = int(_lib.lib().cgp_factor_ws_doubles(self.max_n))
+        ws = torch.empty(max(self.n_obj, 1) * stride, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_factor_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                                   self._p(self.y), self._p(self.y0), self._p(self.y_err), _lib.hptr(h),
+                                                   float(nugget), float(floor), int(flags), self._p(ws),
+                                                   self._p(self._info), self._stream())
+        _lib.check(rc, "cgp_factor_batched_dev")
+        return {"ws": ws, "hyp": h, "nugget": float(nugget), "flags": int(flags)}
+
+    def predict_factored_dev(self, fac, grid, goff=None, new_y0=None, want_var=True):
+        """Prediction from a factor_dev() workspace; same outputs as predict_dev."""
+        m = 0 if goff is not None else int(grid.shape[0])
+        nout = int(goff[-1].item()) if goff is not None else self.n_obj * m
+        mean = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device)
+        var = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device) if want_var else None
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_predict_factored_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                                     _lib.hptr(fac["hyp"]), fac["nugget"], fac["flags"], self._p(fac["ws"]),
+                                                     self._p(self._info), self._p(grid), self._p(goff), m,
+                                                     self._p(new_y0), self._p(mean), self._p(var), self._stream())
+        _lib.check(rc, "cgp_predict_factored_dev")
+        return mean[:nout], (var[:nout] if want_var else None), self._info[:self.n_obj]
+
     def predict(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0):
         """grid: host array, shared (M,[2]) or per-object flat with goff (int64 B+1).
         -> mean, var (host; shape (B,M) for a shared grid, flat otherwise), info."""

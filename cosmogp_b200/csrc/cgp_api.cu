@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 namespace cgp {
@@ -95,6 +96,21 @@ struct HostCall {
   }
   bool sync() { if (err == cudaSuccess) err = cudaStreamSynchronize(st); return err == cudaSuccess; }
 };
+
+// Stream-ordered allocations are recycled instead of being returned to the driver at every
+// synchronisation (the default release threshold is 0): workspaces of ~1 GB per call would
+// otherwise cost milliseconds of cudaMalloc each time.
+static void keep_pool_memory() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ULL;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_for = dev;
+}
 
 static int count_bad(const int* info, int64_t n) {
   int64_t c = 0;
@@ -217,6 +233,34 @@ int cgp_predict_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int di
     if (want > 1) split = (int)want;
   }
   a.split = split;
+  // Many small objects with variances: two kernels.  FACTOR (latency-bound factorisation, L^-1 and
+  // alpha spilled to a workspace) then PREDICT_F (every warp in the DMMA-dense grid phase, factor
+  // staged by TMA) keep the FP64 pipe busier than the fused kernel, whose warps spend half their
+  // life in the factorisation.  Chunks of objects bound the workspace (1.2 GB).
+  static int use_split = -1;
+  if (use_split < 0) { const char* e = getenv("CGP_PREDICT_SPLIT"); use_split = (e && !atoi(e)) ? 0 : 1; }
+  if (use_split && var && max_n <= 64 && n_obj >= 2048 && split == 1) {
+    const int nb = max_n < 1 ? 1 : (max_n + 7) / 8;
+    const int64_t stride = factor_ws_doubles(nb);
+    const int64_t chunk = 65536;
+    double* ws = nullptr;
+    keep_pool_memory();
+    cudaError_t ce = cudaMallocAsync((void**)&ws, (size_t)((n_obj < chunk ? n_obj : chunk) * stride) * sizeof(double), st);
+    if (ce != cudaSuccess) return cuda_fail((int)ce, "cgp_predict_batched_dev (workspace)");
+    int rc2 = 0;
+    for (int64_t c0 = 0; c0 < n_obj && !rc2; c0 += chunk) {
+      SmallArgs f = a;
+      f.n_obj = n_obj - c0 < chunk ? n_obj - c0 : chunk;
+      f.off = off + c0; f.info = info + c0;
+      if (goff) f.goff = goff + c0;
+      else { f.mean = mean + c0 * m_shared; f.var = var + c0 * m_shared; if (new_y0) f.new_y0 = new_y0 + c0 * m_shared; }
+      f.fws = ws; f.fws_stride = stride;
+      rc2 = run_small(TASK_FACTOR, dim, max_n, f, st, "cgp_predict_batched_dev (factor)");
+      if (!rc2) rc2 = run_small(TASK_PREDICT_F, dim, max_n, f, st, "cgp_predict_batched_dev (predict)");
+    }
+    cudaFreeAsync(ws, st);
+    return rc2;
+  }
   return run_small(TASK_PREDICT, dim, max_n, a, st, "cgp_predict_batched_dev");
 }
 
@@ -254,6 +298,50 @@ int cgp_predict_batched_host(int64_t n_obj, const int64_t* off, int dim,
   hc.down(info, b_info, (size_t)n_obj);
   if (!hc.sync()) return cuda_fail((int)hc.err, "cgp_predict_batched_host");
   return count_bad(info, n_obj);
+}
+
+// ------------------------------------------------------------------------------------ factor once, predict many
+int64_t cgp_factor_ws_doubles(int max_n) {
+  if (max_n > 64) return 0;
+  return factor_ws_doubles(max_n < 1 ? 1 : (max_n + 7) / 8);
+}
+
+int cgp_factor_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                           const double* x, const double* y, const double* y0, const double* y_err,
+                           const double* hyp, double nugget, double floor, unsigned flags,
+                           double* ws, int* info, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !ws || !info))) return fail(CGP_ERR_ARG, "cgp_factor_batched_dev: NULL argument");
+  if (max_n <= 0 || max_n > 64) return fail(CGP_ERR_SIZE, "cgp_factor_batched_dev: objects of 1..64 points only (max_n = %d)", max_n);
+  SmallArgs a; memset(&a, 0, sizeof a);
+  int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
+  if (rc) return rc;
+  a.n_obj = n_obj; a.off = off; a.x = x; a.y = y; a.y0 = y0; a.yerr = y_err; a.info = info;
+  a.fws = ws; a.fws_stride = cgp_factor_ws_doubles(max_n); a.split = 1;
+  return run_small(TASK_FACTOR, dim, max_n, a, (cudaStream_t)stream, "cgp_factor_batched_dev");
+}
+
+int cgp_predict_factored_dev(int64_t n_obj, const int64_t* off, int max_n, int dim, const double* x,
+                             const double* hyp, double nugget, unsigned flags, const double* ws, const int* info,
+                             const double* xnew, const int64_t* goff, int64_t m_shared,
+                             const double* new_y0, double* mean, double* var, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !ws || !info || !xnew || !mean)))
+    return fail(CGP_ERR_ARG, "cgp_predict_factored_dev: NULL argument");
+  if (max_n <= 0 || max_n > 64) return fail(CGP_ERR_SIZE, "cgp_predict_factored_dev: objects of 1..64 points only (max_n = %d)", max_n);
+  SmallArgs a; memset(&a, 0, sizeof a);
+  int rc = make_cov(dim, hyp, nugget, 0.0, flags, &a.cov);
+  if (rc) return rc;
+  a.n_obj = n_obj; a.off = off; a.x = x; a.info = const_cast<int*>(info);
+  a.fws = const_cast<double*>(ws); a.fws_stride = cgp_factor_ws_doubles(max_n);
+  a.xnew = xnew; a.goff = goff; a.m_shared = m_shared; a.new_y0 = new_y0; a.mean = mean; a.var = var;
+  int split = 1;
+  if (!goff && n_obj < 296) {
+    const int64_t rbs = (m_shared + 7) / 8;
+    int64_t want = 1628 / (n_obj > 0 ? n_obj : 1), cap = (rbs + 1) / 2;
+    if (want > cap) want = cap;
+    if (want > 1) split = (int)want;
+  }
+  a.split = split;
+  return run_small(TASK_PREDICT_F, dim, max_n, a, (cudaStream_t)stream, "cgp_predict_factored_dev");
 }
 
 // ------------------------------------------------------------------------------------ LOO

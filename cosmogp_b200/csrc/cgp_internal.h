@@ -39,7 +39,9 @@ __host__ __device__ inline Cov cov_from_hyp(int dim, const double* hyp, double n
   return c;
 }
 
-enum Task { TASK_LL = 0, TASK_PREDICT = 1, TASK_LOO = 2, TASK_MATRICES = 3 };
+// TASK_FACTOR writes L^-1 (fragment-order tiles) + alpha per object to a workspace; TASK_PREDICT_F
+// predicts from that workspace (staged into shared memory by one TMA bulk copy per object).
+enum Task { TASK_LL = 0, TASK_PREDICT = 1, TASK_LOO = 2, TASK_MATRICES = 3, TASK_FACTOR = 4, TASK_PREDICT_F = 5 };
 
 struct SmallArgs {
   int64_t n_obj;
@@ -64,6 +66,8 @@ struct SmallArgs {
   double* mean;
   double* var;             // may be null
   int split;               // CTAs per object (each takes every split-th block of 8 grid points)
+  double* fws;             // TASK_FACTOR / TASK_PREDICT_F: factor workspace, fws_stride doubles per object
+  int64_t fws_stride;
   // TASK_LOO
   int loo_mode;
   double* pred; double* pvar; double* pull; double* resid;
@@ -111,6 +115,12 @@ int launch_small64_d1_t2(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d2_t0(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d2_t1(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d2_t2(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d1_t4(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d1_t5(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d2_t4(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d2_t5(int nb, const SmallArgs& a, cudaStream_t stream);
+// doubles per object in the factor workspace for nb blocks of 8 points
+inline int64_t factor_ws_doubles(int nb) { return (int64_t)(nb * (nb + 1) / 2) * 64 + 8 * nb; }
 
 // FP64 ceiling probes (cgp_small.cu)
 int measure_fp64_peak(int kind, double* tflops);

@@ -124,14 +124,26 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   double* noise = px + DIM * LD;
   double* vr = noise + LD;                 // r (LL: becomes z)
   // predict: z overwrites the (dead) noise vector and alpha overwrites r -> same footprint as LL
-  double* vz = (TASK == TASK_PREDICT) ? noise : vr + LD;
-  double* va = (TASK == TASK_PREDICT) ? vr : vz + LD;
+  constexpr bool PRED_LIKE = TASK == TASK_PREDICT || TASK == TASK_FACTOR || TASK == TASK_PREDICT_F;
+  double* vz = PRED_LIKE ? noise : vr + LD;
+  double* va = PRED_LIKE ? vr : vz + LD;
   double* vd = va + LD;
   double* v1 = vd + LD;
   double* vu = v1 + LD;
 
-  const int split = (TASK == TASK_PREDICT) ? a.split : 1;
+  const int split = (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) ? a.split : 1;
   const int64_t n_work = a.n_obj * split;
+  // factor workspace of one object: NT tiles in fragment order followed by alpha (LD doubles)
+  constexpr int WS = NT * TILE + LD;
+  __shared__ __align__(8) unsigned long long s_mbar;       // TMA completion barrier (TASK_PREDICT_F)
+  unsigned mbar_parity = 0;
+  if (TASK == TASK_PREDICT_F) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(&s_mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
 
   // Dynamic work distribution: 11 one-warp CTAs per SM land 3/3/3/2 on the four sub-partitions,
   // so equal static shares would leave the 2-warp partition idle a quarter of the time.
@@ -153,6 +165,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       const bool in = i < nx.n;
       if (DIM == 1) { nx.x[k] = in ? a.x[nx.o0 + i] : 0.0; nx.y2[k] = 0.0; }
       else { nx.x[k] = in ? a.x[2 * (nx.o0 + i)] : 0.0; nx.y2[k] = in ? a.x[2 * (nx.o0 + i) + 1] : 0.0; }
+      if (TASK == TASK_PREDICT_F) { nx.ye[k] = 0.0; nx.r[k] = 0.0; continue; }
       nx.ye[k] = (in && a.yerr) ? a.yerr[nx.o0 + i] : 0.0;
       nx.r[k] = in ? (a.y[nx.o0 + i] - (a.y0 ? a.y0[nx.o0 + i] : 0.0)) : 0.0;
     }
@@ -187,6 +200,30 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     fetch(w_nxt, nx);
     __syncwarp();
     if (TASK == TASK_LOO) rsum = red_g(red_t(rsum));
+    double lp_m = 1.0; int lp_e = 0; int bad = 0;
+    const bool want_u = (TASK == TASK_LOO) && (a.loo_mode == 1);
+    if (TASK == TASK_PREDICT_F) {
+      // L^-1 tiles + alpha of this object: one TMA bulk copy global -> shared, completion on an mbarrier
+      const unsigned mb = (unsigned)__cvta_generic_to_shared(&s_mbar);
+      if (lane == 0) {
+        const unsigned bytes = NT * TILE * 8;
+        const double* src = a.fws + b * a.fws_stride;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer are done
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes + LD * 8) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((unsigned)__cvta_generic_to_shared(tiles)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((unsigned)__cvta_generic_to_shared(va)), "l"(src + NT * TILE), "r"((unsigned)(LD * 8)), "r"(mb) : "memory");
+      }
+      bad = a.info[b];
+      unsigned done = 0;
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mb), "r"(mbar_parity) : "memory");
+      }
+      mbar_parity ^= 1;
+    }
+    if (TASK != TASK_PREDICT_F) {
 
     // ---------------- phase K: covariance tiles, parked in their slots (accumulator values at
     // fragment-order positions).  Two tiles per pass, unrolled twice: 8 exp chains per lane.
@@ -218,7 +255,6 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     __syncwarp();
 
     // ---------------- phase C: left-looking block Cholesky, column by column (static)
-    double lp_m = 1.0; int lp_e = 0; int bad = 0;
 #pragma unroll
     for (int J = 0; J < NB; ++J) {
       double s0[NB], s1[NB], u0[NB], u1[NB];
@@ -343,7 +379,6 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     }
 
     // ---------------- z = L^-1 r (and L^-1 1), alpha = L^-T z, d = colnorm^2(L^-1), u = L^-T L^-1 1
-    const bool want_u = (TASK == TASK_LOO) && (a.loo_mode == 1);
 #pragma unroll
     for (int I = 0; I < NB; ++I) {
       double p = 0.0, p2 = 0.0, p1 = 0.0;
@@ -385,6 +420,18 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     }
     __syncwarp();
     if (lane == 0 && part == 0) a.info[b] = bad;
+    }   // TASK != TASK_PREDICT_F
+
+    if (TASK == TASK_FACTOR) {
+      // ---------------- spill the factor (L^-1 tiles, alpha) for the prediction kernel: 512-byte rows
+      double* dst = a.fws + b * a.fws_stride;
+#pragma unroll 4
+      for (int q = 0; q < NT; ++q)
+        reinterpret_cast<double2*>(dst + q * TILE)[lane] = *reinterpret_cast<const double2*>(tiles + q * TILE + L.fr);
+#pragma unroll
+      for (int i0 = 0; i0 < LD; i0 += 32) { const int i = i0 + lane; if (i < LD) dst[NT * TILE + i] = va[i]; }
+      continue;
+    }
 
     if (TASK == TASK_LOO) {
       const double rho = cov.amp_cross / cov.amp_auto;
@@ -415,7 +462,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       continue;
     }
 
-    if (TASK == TASK_PREDICT) {
+    if (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) {
       // ---------------- two blocks of 8 grid points per pass
       const int64_t g0 = a.goff ? a.goff[b] : 0;
       const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
@@ -716,7 +763,7 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
   }
-  const int64_t n_work = a.n_obj * (TASK == TASK_PREDICT ? a.split : 1);
+  const int64_t n_work = a.n_obj * ((TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) ? a.split : 1);
   static int cap = -1;                                    // experiment knob: CGP_GP64_PER_SM=<blocks per SM>
   if (cap < 0) { const char* e = getenv("CGP_GP64_PER_SM"); cap = e ? atoi(e) : 0; }
   int64_t grid = (int64_t)sm_count * ((cap > 0 && cap < per_sm) ? cap : per_sm);

@@ -335,3 +335,32 @@ def test_c5_pulls_against_batched_oracle(L):
     po = O.loo_batched_1d(x, y, ye, hyp, nug)
     assert_close(pred, po[0].ravel(), RTOL, 1e-12); assert_close(pvar, po[1].ravel(), RTOL, 1e-14)
     assert_close(pull, po[2].ravel(), RTOL, 1e-11); assert_close(resid, po[3].ravel(), RTOL, 1e-12)
+
+
+def test_factor_once_predict_many(L):
+    """cgp_factor_batched_dev + cgp_predict_factored_dev (TMA-staged factor) == fused prediction,
+    for two different grids from one factorisation; also through the internal split of large batches."""
+    import torch
+    from cosmogp_b200.batch import DeviceBatch
+    rng = np.random.default_rng(12)
+    b, n = 3000, 50                        # >= 2048 objects: cgp_predict_batched_dev takes the two-kernel route
+    x = np.sort(rng.uniform(-10, 40, (b, n)), axis=1); y = rng.standard_normal((b, n)); ye = rng.uniform(0.1, 0.3, (b, n))
+    y0 = 0.1 * rng.standard_normal((b, n))
+    hyp, nug = [0.6, 2.5], 0.04
+    batch = DeviceBatch(x.ravel(), y.ravel(), np.arange(b + 1, dtype=np.int64) * n, y0=y0.ravel(), y_err=ye.ravel())
+    fac = batch.factor_dev(hyp, nug)
+    for m in (37, 100):
+        grid = np.linspace(-12, 42, m); ny0 = rng.standard_normal((b, m))
+        mean, var, info = batch.predict_factored_dev(fac, torch.from_numpy(grid).cuda(), None, torch.from_numpy(ny0).cuda(), True)
+        mean = mean.cpu().numpy().reshape(b, m); var = var.cpu().numpy().reshape(b, m)
+        m2, v2, _ = batch.predict(hyp, nug, grid, new_y0=ny0)
+        assert_close(mean, m2, 1e-13, 1e-13); assert_close(var, v2, 1e-13, 1e-14)
+        for i in (0, 1234, 2999):
+            mo, vo = O.predict(y[i], x[i], hyp, nug, grid, ye[i], y0[i], ny0[i], full_cov=False)
+            assert_close(mean[i], mo, RTOL, 1e-12); assert_close(var[i], vo, RTOL, 1e-13)
+    small = DeviceBatch(x[:5].ravel(), y[:5].ravel(), np.arange(6, dtype=np.int64) * n, y0=y0[:5].ravel(), y_err=ye[:5].ravel())
+    grid = np.linspace(-12, 42, 500)
+    ms, vs, _ = small.predict(hyp, nug, grid)                       # few objects: fused kernel with grid split
+    fs = small.factor_dev(hyp, nug)
+    mf, vf, _ = small.predict_factored_dev(fs, torch.from_numpy(grid).cuda(), None, None, True)
+    assert_close(mf.cpu().numpy().reshape(5, 500), ms, 1e-13, 1e-13); assert_close(vf.cpu().numpy().reshape(5, 500), vs, 1e-13, 1e-14)
