@@ -102,14 +102,18 @@ class LargeObject:
         self.log_likelihood = -0.5 * (quad + logdet + self.n * LOG_2PI)      # Gaussian_process.py:68-73
         return self.log_likelihood
 
-    def predict(self, grid, new_y0=None, want_var=True, chunk_rows=4096):
-        """mean (and variance diagonal) on a grid of any length; needs factor() first."""
+    def predict(self, grid, new_y0=None, want_var=True, chunk_rows=None):
+        """mean (and variance diagonal) on a grid of any length; needs factor() first.
+        chunk_rows: grid points per triangular-solve pass (default: as many as fit in ~2 GB of
+        workspace, so that each 128-column GEMM of the solve has hundreds of row tiles)."""
         assert self.alpha is not None, "call factor() first"
         L = _lib.lib()
         g = _t(grid, self.dev)
         m = int(g.shape[0])
         mean = torch.empty(max(m, 1), dtype=torch.float64, device=self.dev)
         var = torch.empty(max(m, 1), dtype=torch.float64, device=self.dev) if want_var else None
+        if chunk_rows is None:
+            chunk_rows = max(128, (2 << 30) // (8 * self.n_pad))
         chunk = min(pad128(m), int(chunk_rows) // 128 * 128 or 128)
         vwork = torch.empty((chunk, self.n_pad), dtype=torch.float64, device=self.dev) if want_var else None
         _lib.check(L.cgp_large_predict_dev(_p(self.a), self.n, self.n_pad, self.n_pad, self.dim, _p(self.x), _p(self.alpha),

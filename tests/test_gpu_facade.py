@@ -139,3 +139,23 @@ def test_not_positive_definite_raises_linalgerror(cg):
     gp = cg.gaussian_process(y, x)
     with pytest.raises(np.linalg.LinAlgError):
         gp.compute_log_likelihood([1.0, 1.0], svd_method=False)
+
+
+def test_streamed_evaluator_matches_resident_batch(cg):
+    """The pipelined end-to-end path (chunks over 3 streams) returns bit-identical results."""
+    from cosmogp_b200.batch import DeviceBatch, StreamedEvaluator
+    rng = np.random.default_rng(0)
+    b, n, m = 5003, 60, 100
+    x = np.sort(rng.uniform(-10, 40, (b, n)), axis=1); y = rng.standard_normal((b, n)); ye = np.full((b, n), 0.2)
+    y0 = 0.1 * rng.standard_normal((b, n)); ny0 = rng.standard_normal((b, m))
+    ev = StreamedEvaluator(b, n, m, n_chunks=7)
+    for k, v in (("x", x), ("y", y), ("y0", y0), ("y_err", ye), ("new_y0", ny0)):
+        ev.host(k)[...] = v
+    grid = np.linspace(-10, 40, m)
+    tot, ll, mean, var, info = ev.run([0.5, 2.0], 0.03, grid)
+    batch = DeviceBatch(x.ravel(), y.ravel(), np.arange(b + 1) * n, y0=y0.ravel(), y_err=ye.ravel())
+    t2, ll2, _ = batch.log_likelihood([0.5, 2.0], 0.03)
+    m2, v2, _ = batch.predict([0.5, 2.0], 0.03, grid, new_y0=ny0)
+    assert not info.any() and tot == t2
+    assert np.array_equal(ll, ll2) and np.array_equal(mean, m2) and np.array_equal(var, v2)
+    assert ev.h2d_bytes == b * (4 * n + m) * 8 and ev.d2h_bytes == b * (8 + 16 * m + 4)

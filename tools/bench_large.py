@@ -73,7 +73,7 @@ obj = dense.LargeObject(x, y, ye, None, dim=2)
 hyp = [1.0, 30.0, 25.0, 50.0]
 ms_fac = timed(lambda: obj.factor(hyp, 0.0))
 g = torch.from_numpy(grid).cuda(); mean = torch.empty(m, dtype=torch.float64, device="cuda"); var = torch.empty_like(mean)
-chunk = 8192
+chunk = 131072 if m > 100000 else (m + 127) // 128 * 128
 vwork = torch.empty((chunk, obj.n_pad), dtype=torch.float64, device="cuda")
 h = np.ascontiguousarray(hyp, dtype=np.float64)
 ms_mean = timed(lambda: L.cgp_large_predict_dev(obj.a.data_ptr(), n, obj.n_pad, obj.n_pad, 2, obj.x.data_ptr(), obj.alpha.data_ptr(), h.ctypes.data, 0.0, 0, g.data_ptr(), m, None, mean.data_ptr(), None, None, 0, st))
