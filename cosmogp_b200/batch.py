@@ -119,27 +119,40 @@ class DeviceBatch:
 
     def ll_objhyp(self, hyp_rows, idx, nugget_rows=None, nugget=0.0, floor=0.0, flags=0):
         """Log-likelihood of the objects `idx` (int array), object idx[k] using its own
-        hyperparameters hyp_rows[k] (and nugget_rows[k]).  -> (ll (k,), info (k,)) host arrays."""
-        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        hyperparameters hyp_rows[k] (and nugget_rows[k]).  -> (ll (k,), info (k,)) host arrays.
+        Compact I/O: only the k active rows cross PCIe, through persistent pinned / device buffers."""
         k, nh = len(idx), (2 if self.dim == 1 else 4)
         if k == 0:
             return np.zeros(0), np.zeros(0, dtype=np.int32)
-        full = np.zeros((self.n_obj, nh)); full[idx] = np.asarray(hyp_rows, dtype=np.float64).reshape(k, nh)
-        hd = self._up(full)
+        c = getattr(self, "_oh", None)
+        if c is None:
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+            dev = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.device)
+            b = max(self.n_obj, 1)
+            c = self._oh = {"hyp_h": pin((b, nh), torch.float64), "hyp_d": dev((b, nh), torch.float64),
+                            "nug_h": pin((b,), torch.float64), "nug_d": dev((b,), torch.float64),
+                            "ord_h": pin((b,), torch.int32), "ord_d": dev((b,), torch.int32),
+                            "ll_h": pin((b,), torch.float64), "ll_d": dev((b,), torch.float64),
+                            "info_h": pin((b,), torch.int32), "info_d": dev((b,), torch.int32)}
+        c["hyp_h"].numpy()[:k] = np.asarray(hyp_rows, dtype=np.float64).reshape(k, nh)
+        c["ord_h"].numpy()[:k] = idx
+        c["hyp_d"][:k].copy_(c["hyp_h"][:k], non_blocking=True)
+        c["ord_d"][:k].copy_(c["ord_h"][:k], non_blocking=True)
         nd = None
         if nugget_rows is not None:
-            fn = np.zeros(self.n_obj); fn[idx] = np.asarray(nugget_rows, dtype=np.float64)
-            nd = self._up(fn)
-        order = self._up(idx.astype(np.int32)) if k < self.n_obj or not np.array_equal(idx, np.arange(k)) else None
-        ll = torch.empty(max(self.n_obj, 1), dtype=torch.float64, device=self.device)
+            c["nug_h"].numpy()[:k] = nugget_rows
+            c["nug_d"][:k].copy_(c["nug_h"][:k], non_blocking=True)
+            nd = c["nug_d"]
         with torch.cuda.device(self.device):
             rc = _lib.lib().cgp_ll_objhyp_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
-                                              self._p(self.y), self._p(self.y0), self._p(self.y_err), self._p(hd),
-                                              self._p(nd), float(nugget), float(floor), int(flags), self._p(order), k,
-                                              self._p(ll), self._p(self._info), self._stream())
+                                              self._p(self.y), self._p(self.y0), self._p(self.y_err), self._p(c["hyp_d"]),
+                                              self._p(nd), float(nugget), float(floor), int(flags), self._p(c["ord_d"]), k,
+                                              self._p(c["ll_d"]), self._p(c["info_d"]), self._stream())
         _lib.check(rc, "cgp_ll_objhyp_dev")
-        ll_h = self._down(ll[:self.n_obj]); info_h = self._down(self._info[:self.n_obj])
-        return ll_h[idx], info_h[idx]
+        c["ll_h"][:k].copy_(c["ll_d"][:k], non_blocking=True)
+        c["info_h"][:k].copy_(c["info_d"][:k], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return c["ll_h"].numpy()[:k].copy(), c["info_h"].numpy()[:k].copy()
 
     def predict_dev(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0):
         h = self._hyp(hyp)

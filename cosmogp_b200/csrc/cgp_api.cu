@@ -202,6 +202,7 @@ int cgp_ll_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
   a.x = x; a.y = y; a.y0 = y0; a.yerr = y_err; a.ll = ll_obj; a.info = info;
   a.hyp_obj = hyp_obj; a.n_hyp = dim == 1 ? 2 : 4; a.nugget_obj = nugget_obj; a.nugget_shared = nugget;
   a.floor_shared = floor; a.flags = flags;
+  a.compact_io = order ? 1 : 0;
   a.cov = Cov();
   return run_small(TASK_LL, dim, max_n, a, (cudaStream_t)stream, "cgp_ll_objhyp_dev");
 }

@@ -55,6 +55,7 @@ struct SmallArgs {
   // per-object hyperparameters (lock-step per-object fits): when hyp_obj != null object b uses
   // hyp_obj[b*n_hyp ..] and nugget_obj[b] (or nugget_shared) instead of `cov`
   const double* hyp_obj; int n_hyp; const double* nugget_obj; double nugget_shared; double floor_shared; unsigned flags;
+  int compact_io;          // with `order`: hyp_obj / nugget_obj / ll / info are indexed by position in `order`, not by object id
   int* info;               // [n_obj]
   // TASK_LL
   double* ll;              // [n_obj]

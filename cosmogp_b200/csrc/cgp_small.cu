@@ -188,7 +188,8 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
     const int n = (int)(a.off[b + 1] - o0);
     const int nb = (n + 7) >> 3;
     const double* amat = a.amat ? a.amat + a.aoff[b] : nullptr;
-    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + b * a.n_hyp, a.nugget_obj ? a.nugget_obj[b] : a.nugget_shared,
+    const int64_t io = a.compact_io ? oi : b;
+    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + io * a.n_hyp, a.nugget_obj ? a.nugget_obj[io] : a.nugget_shared,
                                       a.floor_shared, a.flags);
 
     // ---------------- stage the object
@@ -299,9 +300,9 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
         quad = red_warp(quad);
         if (lane == 0) {
           const int bad = s_bad;
-          a.info[b] = bad;
+          a.info[io] = bad;
           const double logdet = log(lp_m) + (double)lp_e * 0.693147180559945309417232;
-          a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+          a.ll[io] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
         }
       }
       continue;

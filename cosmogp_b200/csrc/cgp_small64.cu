@@ -181,7 +181,8 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     const int64_t b = a.order ? a.order[oi] : oi;
     const int64_t o0 = nx.o0;
     const int n = nx.n;
-    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + b * a.n_hyp, a.nugget_obj ? a.nugget_obj[b] : a.nugget_shared,
+    const int64_t io = a.compact_io ? oi : b;
+    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + io * a.n_hyp, a.nugget_obj ? a.nugget_obj[io] : a.nugget_shared,
                                       a.floor_shared, a.flags);
 
     // ---------------- stage (from the prefetched registers), then start the next object's loads
@@ -336,9 +337,9 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       }
       quad = red_g(red_t(quad));
       if (lane == 0) {
-        a.info[b] = bad;
+        a.info[io] = bad;
         const double logdet = log(lp_m) + (double)lp_e * LN2;
-        a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+        a.ll[io] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
       }
       continue;
     }
@@ -585,11 +586,12 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   const int64_t n_work = a.n_obj;
 
   constexpr int NR = (LD + 31) / 32;
-  struct Next { int64_t b; int n; double x[NR], y2[NR], r[NR], ye[NR]; };
+  struct Next { int64_t b, io; int n; double x[NR], y2[NR], r[NR], ye[NR]; };
   auto fetch = [&](int64_t w, Next& nx) {
-    nx.n = -1; nx.b = 0;
+    nx.n = -1; nx.b = 0; nx.io = 0;
     if (w >= n_work) return;
     nx.b = a.order ? a.order[w] : w;
+    nx.io = a.compact_io ? w : nx.b;
     const int64_t o0 = a.off[nx.b];
     nx.n = (int)(a.off[nx.b + 1] - o0);
 #pragma unroll
@@ -608,9 +610,9 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   for (;; w = w_nxt, w_nxt = __shfl_sync(FULL, t_next, 0)) {
     if (w >= n_work) break;
     if (lane == 0) t_next = (int64_t)atomicAdd(ticket, 1ULL) + 2 * (int64_t)gridDim.x;
-    const int64_t b = nx.b;
+    const int64_t io = nx.io;
     const int n = nx.n;
-    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + b * a.n_hyp, a.nugget_obj ? a.nugget_obj[b] : a.nugget_shared,
+    if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + io * a.n_hyp, a.nugget_obj ? a.nugget_obj[io] : a.nugget_shared,
                                       a.floor_shared, a.flags);
     __syncwarp();
 #pragma unroll
@@ -709,9 +711,9 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     });
     quad = red_g(red_t(quad));
     if (lane == 0) {
-      a.info[b] = bad;
+      a.info[io] = bad;
       const double logdet = log(lp_m) + (double)lp_e * LN2;
-      a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+      a.ll[io] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
     }
   }
 }

@@ -7,7 +7,8 @@ cosmogp/Gaussian_process.py:216-253 -> scipy.optimize.fmin).  Here scipy's Nelde
 replayed for ALL objects at once on the host: every simplex operation is a vectorised numpy
 step and every objective evaluation is ONE batched device launch in which each object uses
 its own trial hyperparameters (cgp_ll_objhyp_dev).  Each object follows exactly the decisions
-scipy would take for it; objects that have converged drop out of the launches.
+scipy would take for it; converged objects are dropped from the working set, so the host
+arithmetic and the launches shrink as the batch converges.
 """
 import numpy as np
 
@@ -26,71 +27,80 @@ def nelder_mead_lockstep(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfun=N
     nonzdelt, zdelt = 0.05, 0.00025
     maxiter = n * 200 if maxiter is None else maxiter
     maxfun = n * 200 if maxfun is None else maxfun
-    allidx = np.arange(B, dtype=np.int64)
 
-    sim = np.empty((B, n + 1, n))
-    sim[:, 0] = x0
+    x_out = np.empty((B, n)); f_out = np.empty(B)
+    it_out = np.empty(B, dtype=np.int64); fc_out = np.empty(B, dtype=np.int64)
+
+    # working set (compact): ids, simplex S (k, n+1, n), values F (k, n+1), counters
+    ids = np.arange(B, dtype=np.int64)
+    S = np.empty((B, n + 1, n))
+    S[:, 0] = x0
     for k in range(n):
         yk = x0.copy()
         yk[:, k] = np.where(yk[:, k] != 0, (1 + nonzdelt) * yk[:, k], zdelt)
-        sim[:, k + 1] = yk
-    fsim = np.empty((B, n + 1))
+        S[:, k + 1] = yk
+    F = np.empty((B, n + 1))
     for k in range(n + 1):
-        fsim[:, k] = fun(sim[:, k], allidx)
-    fcalls = np.full(B, n + 1, dtype=np.int64)
-    order = np.argsort(fsim, axis=1, kind="stable")
-    fsim = np.take_along_axis(fsim, order, axis=1)
-    sim = np.take_along_axis(sim, order[:, :, None], axis=1)
-    iterations = np.ones(B, dtype=np.int64)
-    active = np.ones(B, dtype=bool)
+        F[:, k] = fun(S[:, k], ids)
+    fc = np.full(B, n + 1, dtype=np.int64)
+    it = np.ones(B, dtype=np.int64)
+
+    def sort_rows(S, F):
+        order = np.argsort(F, axis=1, kind="stable")
+        return np.take_along_axis(S, order[:, :, None], axis=1), np.take_along_axis(F, order, axis=1)
+
+    S, F = sort_rows(S, F)
 
     def evaluate(points, mask):
-        """objective at points[mask] -> full-length array (NaN elsewhere); counts the calls."""
-        out = np.full(B, np.nan)
-        idx = allidx[mask]
-        if len(idx):
-            out[mask] = fun(points[mask], idx)
-            fcalls[mask] += 1
+        """objective at points[mask] (NaN elsewhere); counts the calls."""
+        out = np.full(len(ids), np.nan)
+        if mask.any():
+            out[mask] = fun(points[mask], ids[mask])
+            fc[mask] += 1
         return out
 
-    while True:
-        active &= (fcalls < maxfun) & (iterations < maxiter)
-        done = (np.max(np.abs(sim[:, 1:] - sim[:, :1]), axis=(1, 2)) <= xatol) & \
-               (np.max(np.abs(fsim[:, :1] - fsim[:, 1:]), axis=1) <= fatol)
-        active &= ~done
-        if not active.any():
-            break
-        xbar = np.add.reduce(sim[:, :-1], axis=1) / n
-        xr = (1 + rho) * xbar - rho * sim[:, -1]
-        fxr = evaluate(xr, active)
+    while len(ids):
+        k = len(ids)
+        spread = np.abs(S[:, 1:] - S[:, :1]).reshape(k, -1).max(axis=1)
+        fspread = np.abs(F[:, :1] - F[:, 1:]).max(axis=1)
+        keep = (fc < maxfun) & (it < maxiter) & ~((spread <= xatol) & (fspread <= fatol))
+        if not keep.all():
+            fin = ~keep
+            x_out[ids[fin]] = S[fin, 0]; f_out[ids[fin]] = F[fin, 0]
+            it_out[ids[fin]] = it[fin]; fc_out[ids[fin]] = fc[fin]
+            ids, S, F, fc, it = ids[keep], S[keep], F[keep], fc[keep], it[keep]
+            if not len(ids):
+                break
+        everyone = np.ones(len(ids), dtype=bool)
+        worst = S[:, -1]
+        xbar = np.add.reduce(S[:, :-1], axis=1) / n
+        xr = (1 + rho) * xbar - rho * worst
+        fxr = evaluate(xr, everyone)
         with np.errstate(invalid="ignore"):
-            lt_best = active & (fxr < fsim[:, 0])
-            mid = active & ~lt_best & (fxr < fsim[:, -2])
-            rest = active & ~lt_best & ~mid
-            out_c = rest & (fxr < fsim[:, -1])          # outside contraction
-            in_c = rest & ~out_c                         # inside contraction
+            lt_best = fxr < F[:, 0]
+            mid = ~lt_best & (fxr < F[:, -2])
+            rest = ~lt_best & ~mid
+            out_c = rest & (fxr < F[:, -1])              # outside contraction
+            in_c = rest & ~out_c                          # inside contraction
         # second evaluation: expansion / outside contraction / inside contraction, one launch
-        x2 = np.where(lt_best[:, None], (1 + rho * chi) * xbar - rho * chi * sim[:, -1],
-                      np.where(out_c[:, None], (1 + psi * rho) * xbar - psi * rho * sim[:, -1],
-                               (1 - psi) * xbar + psi * sim[:, -1]))
-        need2 = lt_best | out_c | in_c
-        f2 = evaluate(x2, need2)
+        x2 = np.where(lt_best[:, None], (1 + rho * chi) * xbar - rho * chi * worst,
+                      np.where(out_c[:, None], (1 + psi * rho) * xbar - psi * rho * worst,
+                               (1 - psi) * xbar + psi * worst))
+        f2 = evaluate(x2, lt_best | out_c | in_c)
         with np.errstate(invalid="ignore"):
             take_e = lt_best & (f2 < fxr)
             take_r = (lt_best & ~take_e) | mid
             take_oc = out_c & (f2 <= fxr)
-            take_ic = in_c & (f2 < fsim[:, -1])
+            take_ic = in_c & (f2 < F[:, -1])
             shrink = (out_c & ~take_oc) | (in_c & ~take_ic)
         take2 = take_e | take_oc | take_ic
-        sim[take2, -1] = x2[take2]; fsim[take2, -1] = f2[take2]
-        sim[take_r, -1] = xr[take_r]; fsim[take_r, -1] = fxr[take_r]
+        S[take2, -1] = x2[take2]; F[take2, -1] = f2[take2]
+        S[take_r, -1] = xr[take_r]; F[take_r, -1] = fxr[take_r]
         if shrink.any():
             for j in range(1, n + 1):
-                sim[shrink, j] = sim[shrink, 0] + sigma * (sim[shrink, j] - sim[shrink, 0])
-                fj = evaluate(sim[:, j], shrink)
-                fsim[shrink, j] = fj[shrink]
-        order = np.argsort(fsim[active], axis=1, kind="stable")
-        fsim[active] = np.take_along_axis(fsim[active], order, axis=1)
-        sim[active] = np.take_along_axis(sim[active], order[:, :, None], axis=1)
-        iterations[active] += 1
-    return sim[:, 0].copy(), fsim[:, 0].copy(), iterations, fcalls
+                S[shrink, j] = S[shrink, 0] + sigma * (S[shrink, j] - S[shrink, 0])
+                fj = evaluate(S[:, j], shrink)
+                F[shrink, j] = fj[shrink]
+        S, F = sort_rows(S, F)
+        it += 1
+    return x_out, f_out, it_out, fc_out

@@ -76,8 +76,9 @@ int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
 
 /* ---- per-object fits: one likelihood evaluation where object b uses its OWN hyperparameters
  *      hyp_obj[b*nh .. b*nh+nh) (nh = 2 or 4) and nugget_obj[b] (NULL -> the shared `nugget`).
- *      order (device, may be NULL) restricts the evaluation to n_active object ids; ll_obj / info
- *      are indexed by object id.  This is the batched form of the reference's per-object loop
+ *      order (device, may be NULL) restricts the evaluation to n_active object ids; hyp_obj,
+ *      nugget_obj, ll_obj and info are then COMPACT (entry k belongs to object order[k]); without
+ *      order they are indexed by object id.  This is the batched form of the reference's per-object loop
  *      `gaussian_process(y[i], x[i]).find_hyperparameters()` (docs/notebook/1D_kernel_example_with_noise.ipynb
  *      cell 13): scipy's Nelder-Mead runs in lock step over all objects on the host. */
 int cgp_ll_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
