@@ -37,6 +37,36 @@ def pack_csr(seq, dim=1):
     return flat, off
 
 
+class RaggedView(object):
+    """list-like view of per-object slices of a flat array (what the reference keeps as a Python
+    list of arrays), built in O(1): at 10^6 objects a real list of slices costs seconds."""
+
+    def __init__(self, flat, off):
+        self.flat, self.off = flat, np.asarray(off, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.off) - 1
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return self.flat[self.off[i]:self.off[i + 1]]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def extended(self, flat, off):
+        """view over this view's data followed by another batch (compute_pull appends across calls)."""
+        off = np.asarray(off, dtype=np.int64)
+        if len(self) == 0:
+            return RaggedView(flat, off)
+        return RaggedView(np.concatenate([self.flat, flat]), np.concatenate([self.off, off[1:] + self.off[-1]]))
+
+
 def pinned_like(a):
     """Copy a numpy array into pinned host memory (returns the numpy view and its owner)."""
     t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int64, pin_memory=True)

@@ -22,7 +22,7 @@ from scipy.optimize import fmin
 
 from . import _lib
 from . import mean as _mean
-from .batch import DeviceBatch, pack_csr
+from .batch import DeviceBatch, RaggedView, pack_csr
 from .kernel import init_rbf, rbf_kernel_1d, rbf_kernel_2d
 
 
@@ -90,7 +90,7 @@ class Gaussian_process:
         if self.substract_mean or self.Mean_Y is not None:                  # :180-186
             self._y0_flat, self._diff_used = _mean.batched_mean(
                 self._x_flat, self._y_flat, self._off, self._dim, self.Mean_Y, self.Time_mean, self.diff)
-            self.y0 = [self._y0_flat[self._off[i]:self._off[i + 1]] for i in range(self.N_sn)]
+            self.y0 = RaggedView(self._y0_flat, self._off)
         else:
             self._y0_flat, self._diff_used = None, np.zeros(self.N_sn)
             self.y0 = np.zeros(self.N_sn)
@@ -219,8 +219,8 @@ class Gaussian_process:
             mean, var, info = self.batch.predict(hyp, nug, grid, goff=goff, new_y0=new_y0,
                                                  want_var=want_var, flags=self.flags)
             self._raise_if_bad(info)
-            self.Prediction = [mean[goff[i]:goff[i + 1]] for i in range(self.N_sn)]
-            self.prediction_variance = [var[goff[i]:goff[i + 1]] for i in range(self.N_sn)] if want_var else None
+            self.Prediction = RaggedView(mean, goff)
+            self.prediction_variance = RaggedView(var, goff) if want_var else None
         else:
             self.as_the_same_time = False
             self.new_binning = new_binning

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib
 from . import mean as _mean
-from .batch import DeviceBatch, pack_csr
+from .batch import DeviceBatch, RaggedView, pack_csr
 
 
 class build_pull:
@@ -30,10 +30,11 @@ class build_pull:
 
         self.n_object = len(y)
 
-        self._pull = []
+        empty = np.zeros(1, dtype=np.int64)
+        self._pull = RaggedView(np.zeros(0), empty)       # per object, list-like (views, no 10^6-element list)
         self.pull = np.zeros(0)          # flat, grows with every compute_pull call like the reference lists
         self.residual = np.zeros(0)
-        self.prediction = []
+        self.prediction = RaggedView(np.zeros(0), empty)
 
         self.pull_average = None
         self.pull_std = None
@@ -73,12 +74,11 @@ class build_pull:
         if len(bad):
             raise np.linalg.LinAlgError("covariance of object %d is not positive definite" % int(bad[0]))
 
-        for sn in range(self.n_object):
-            self._pull.append(pull[off[sn]:off[sn + 1]])
-            self.prediction.append(pred[off[sn]:off[sn + 1]])
+        self._pull = self._pull.extended(pull, off)
+        self.prediction = self.prediction.extended(pred, off)
         self.prediction_variance = pvar
-        self.pull = np.concatenate([self.pull, pull])
-        self.residual = np.concatenate([self.residual, resid])
+        self.pull = pull if not len(self.pull) else np.concatenate([self.pull, pull])
+        self.residual = resid if not len(self.residual) else np.concatenate([self.residual, resid])
 
         # scipy.stats.norm.fit (pull.py:102) = sample mean and population standard deviation
         self.pull_average = float(np.mean(self.pull))
