@@ -184,7 +184,31 @@ class DeviceBatch:
         torch.cuda.current_stream(self.device).synchronize()
         return c["ll_h"].numpy()[:k].copy(), c["info_h"].numpy()[:k].copy()
 
+    def _objhyp(self, hyp, nugget):
+        """(B, nh) hyperparameters (+ optional (B,) nuggets) -> device tensors, or None for shared ones."""
+        if np.ndim(hyp) != 2:
+            return None
+        nh = 2 if self.dim == 1 else 4
+        h = np.ascontiguousarray(hyp, dtype=np.float64)
+        assert h.shape == (self.n_obj, nh), "per-object hyperparameters must have shape (%d, %d)" % (self.n_obj, nh)
+        nd = self._up(np.ascontiguousarray(nugget, dtype=np.float64)) if np.ndim(nugget) == 1 else None
+        return self._up(h), nd, (0.0 if nd is not None else float(nugget))
+
     def predict_dev(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0):
+        oh = self._objhyp(hyp, nugget)
+        if oh is not None:
+            m = 0 if goff is not None else int(grid.shape[0])
+            nout = int(goff[-1].item()) if goff is not None else self.n_obj * m
+            mean = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device)
+            var = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device) if want_var else None
+            with torch.cuda.device(self.device):
+                rc = _lib.lib().cgp_predict_objhyp_dev(self.n_obj, self._p(self.off), self.max_n, self.dim,
+                                                       self._p(self.x), self._p(self.y), self._p(self.y0), self._p(self.y_err),
+                                                       self._p(oh[0]), self._p(oh[1]), oh[2], float(floor), int(flags),
+                                                       self._p(grid), self._p(goff), m, self._p(new_y0),
+                                                       self._p(mean), self._p(var), self._p(self._info), self._stream())
+            _lib.check(rc, "cgp_predict_objhyp_dev")
+            return mean[:nout], (var[:nout] if want_var else None), self._info[:self.n_obj]
         h = self._hyp(hyp)
         m = 0 if goff is not None else int(grid.shape[0])
         nout = int(goff[-1].item()) if goff is not None else self.n_obj * m
@@ -247,9 +271,19 @@ class DeviceBatch:
     def loo(self, hyp, nugget, mean=None, mode=_lib.CGP_LOO_PLAIN, floor=0.0, flags=0):
         """Closed-form leave-one-out; `mean` (flat, host) replaces the batch's y0 when given.
         -> pred, pred_var, pull, resid (flat host arrays), info."""
-        h = self._hyp(hyp)
         m = self._up(np.asarray(mean, dtype=np.float64)) if mean is not None else self.y0
         outs = [torch.empty(max(self.n_pts, 1), dtype=torch.float64, device=self.device) for _ in range(4)]
+        oh = self._objhyp(hyp, nugget)
+        if oh is not None:
+            with torch.cuda.device(self.device):
+                rc = _lib.lib().cgp_loo_objhyp_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                                   self._p(self.y), self._p(m), self._p(self.y_err), self._p(oh[0]),
+                                                   self._p(oh[1]), oh[2], float(floor), int(flags), int(mode),
+                                                   *[self._p(o) for o in outs], self._p(self._info), self._stream())
+            _lib.check(rc, "cgp_loo_objhyp_dev")
+            res = [self._down(o[:self.n_pts]) for o in outs]
+            return res + [self._down(self._info[:self.n_obj])]
+        h = self._hyp(hyp)
         with torch.cuda.device(self.device):
             rc = _lib.lib().cgp_loo_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
                                                 self._p(self.y), self._p(m), self._p(self.y_err), _lib.hptr(h),

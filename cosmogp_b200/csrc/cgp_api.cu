@@ -208,17 +208,28 @@ int cgp_ll_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
 }
 
 // ------------------------------------------------------------------------------------ predict
-int cgp_predict_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
-                            const double* x, const double* y, const double* y0, const double* y_err,
-                            const double* hyp, double nugget, double floor, unsigned flags,
-                            const double* xnew, const int64_t* goff, int64_t m_shared,
-                            const double* new_y0, double* mean, double* var, int* info, void* stream) {
+// hyp (shared) or hyp_obj / nugget_obj (per object, device arrays indexed by object id)
+static void set_objhyp(SmallArgs& a, int dim, const double* hyp_obj, const double* nugget_obj, double nugget,
+                       double floor, unsigned flags) {
+  a.hyp_obj = hyp_obj; a.n_hyp = dim == 1 ? 2 : 4; a.nugget_obj = nugget_obj; a.nugget_shared = nugget;
+  a.floor_shared = floor; a.flags = flags; a.compact_io = 0;
+}
+
+static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                        const double* x, const double* y, const double* y0, const double* y_err,
+                        const double* hyp, const double* hyp_obj, const double* nugget_obj,
+                        double nugget, double floor, unsigned flags,
+                        const double* xnew, const int64_t* goff, int64_t m_shared,
+                        const double* new_y0, double* mean, double* var, int* info, void* stream) {
   if (n_obj < 0 || (n_obj && (!off || !x || !y || !xnew || !mean || !info)))
     return fail(CGP_ERR_ARG, "cgp_predict_batched_dev: NULL argument");
   if (!goff && m_shared < 0) return fail(CGP_ERR_ARG, "cgp_predict_batched_dev: m_shared < 0");
+  if (dim != 1 && dim != 2) return fail(CGP_ERR_ARG, "dim must be 1 or 2, got %d", dim);
   cudaStream_t st = (cudaStream_t)stream;
   SmallArgs a; memset(&a, 0, sizeof a);
-  int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
+  int rc = 0;
+  if (hyp_obj) set_objhyp(a, dim, hyp_obj, nugget_obj, nugget, floor, flags);
+  else rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
   if (rc) return rc;
   if (n_obj && max_n <= 0 && (rc = max_n_from_device(n_obj, off, st, &max_n))) return rc;
   a.n_obj = n_obj; a.off = off; a.x = x; a.y = y; a.y0 = y0; a.yerr = y_err; a.info = info;
@@ -256,6 +267,7 @@ int cgp_predict_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int di
       if (goff) f.goff = goff + c0;
       else { f.mean = mean + c0 * m_shared; f.var = var + c0 * m_shared; if (new_y0) f.new_y0 = new_y0 + c0 * m_shared; }
       f.fws = ws; f.fws_stride = stride;
+      if (hyp_obj) { f.hyp_obj = hyp_obj + c0 * f.n_hyp; if (nugget_obj) f.nugget_obj = nugget_obj + c0; }
       rc2 = run_small(TASK_FACTOR, dim, max_n, f, st, "cgp_predict_batched_dev (factor)");
       if (!rc2) rc2 = run_small(TASK_PREDICT_F, dim, max_n, f, st, "cgp_predict_batched_dev (predict)");
     }
@@ -263,6 +275,25 @@ int cgp_predict_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int di
     return rc2;
   }
   return run_small(TASK_PREDICT, dim, max_n, a, st, "cgp_predict_batched_dev");
+}
+
+int cgp_predict_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                            const double* x, const double* y, const double* y0, const double* y_err,
+                            const double* hyp, double nugget, double floor, unsigned flags,
+                            const double* xnew, const int64_t* goff, int64_t m_shared,
+                            const double* new_y0, double* mean, double* var, int* info, void* stream) {
+  return predict_impl(n_obj, off, max_n, dim, x, y, y0, y_err, hyp, nullptr, nullptr, nugget, floor, flags,
+                      xnew, goff, m_shared, new_y0, mean, var, info, stream);
+}
+
+int cgp_predict_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                           const double* x, const double* y, const double* y0, const double* y_err,
+                           const double* hyp_obj, const double* nugget_obj, double nugget, double floor, unsigned flags,
+                           const double* xnew, const int64_t* goff, int64_t m_shared,
+                           const double* new_y0, double* mean, double* var, int* info, void* stream) {
+  if (!hyp_obj) return fail(CGP_ERR_ARG, "cgp_predict_objhyp_dev: hyp_obj is NULL");
+  return predict_impl(n_obj, off, max_n, dim, x, y, y0, y_err, nullptr, hyp_obj, nugget_obj, nugget, floor, flags,
+                      xnew, goff, m_shared, new_y0, mean, var, info, stream);
 }
 
 int cgp_predict_batched_host(int64_t n_obj, const int64_t* off, int dim,
@@ -346,22 +377,45 @@ int cgp_predict_factored_dev(int64_t n_obj, const int64_t* off, int max_n, int d
 }
 
 // ------------------------------------------------------------------------------------ LOO
-int cgp_loo_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
-                        const double* x, const double* y, const double* m, const double* y_err,
-                        const double* hyp, double nugget, double floor, unsigned flags, int mode,
-                        double* pred, double* pred_var, double* pull, double* resid,
-                        int* info, void* stream) {
+static int loo_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                    const double* x, const double* y, const double* m, const double* y_err,
+                    const double* hyp, const double* hyp_obj, const double* nugget_obj,
+                    double nugget, double floor, unsigned flags, int mode,
+                    double* pred, double* pred_var, double* pull, double* resid,
+                    int* info, void* stream) {
   if (n_obj < 0 || (n_obj && (!off || !x || !y || !info)))
     return fail(CGP_ERR_ARG, "cgp_loo_batched_dev: NULL argument");
   if (mode != CGP_LOO_PLAIN && mode != CGP_LOO_RECENTER) return fail(CGP_ERR_ARG, "cgp_loo_batched_dev: bad mode %d", mode);
+  if (dim != 1 && dim != 2) return fail(CGP_ERR_ARG, "dim must be 1 or 2, got %d", dim);
   cudaStream_t st = (cudaStream_t)stream;
   SmallArgs a; memset(&a, 0, sizeof a);
-  int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
+  int rc = 0;
+  if (hyp_obj) set_objhyp(a, dim, hyp_obj, nugget_obj, nugget, floor, flags);
+  else rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
   if (rc) return rc;
   if (n_obj && max_n <= 0 && (rc = max_n_from_device(n_obj, off, st, &max_n))) return rc;
   a.n_obj = n_obj; a.off = off; a.x = x; a.y = y; a.y0 = m; a.yerr = y_err; a.info = info;
   a.loo_mode = mode; a.pred = pred; a.pvar = pred_var; a.pull = pull; a.resid = resid;
   return run_small(TASK_LOO, dim, max_n, a, st, "cgp_loo_batched_dev");
+}
+
+int cgp_loo_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                        const double* x, const double* y, const double* m, const double* y_err,
+                        const double* hyp, double nugget, double floor, unsigned flags, int mode,
+                        double* pred, double* pred_var, double* pull, double* resid,
+                        int* info, void* stream) {
+  return loo_impl(n_obj, off, max_n, dim, x, y, m, y_err, hyp, nullptr, nullptr, nugget, floor, flags, mode,
+                  pred, pred_var, pull, resid, info, stream);
+}
+
+int cgp_loo_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                       const double* x, const double* y, const double* m, const double* y_err,
+                       const double* hyp_obj, const double* nugget_obj, double nugget, double floor, unsigned flags,
+                       int mode, double* pred, double* pred_var, double* pull, double* resid,
+                       int* info, void* stream) {
+  if (!hyp_obj) return fail(CGP_ERR_ARG, "cgp_loo_objhyp_dev: hyp_obj is NULL");
+  return loo_impl(n_obj, off, max_n, dim, x, y, m, y_err, nullptr, hyp_obj, nugget_obj, nugget, floor, flags, mode,
+                  pred, pred_var, pull, resid, info, stream);
 }
 
 int cgp_loo_batched_host(int64_t n_obj, const int64_t* off, int dim,

@@ -200,12 +200,17 @@ class Gaussian_process:
         return k[0], kinv[0]
 
     # ------------------------------------------------------------------ prediction
-    def get_prediction(self, new_binning=None, COV=True, svd_method=True):
+    def get_prediction(self, new_binning=None, COV=True, svd_method=True, per_object=False):
         """Interpolation (and its covariance) on a new grid (:270-361).
 
         new_binning None -> each object's own epochs.  COV: True (full matrices on
-        access + diagonal), 'diag' (diagonal only) or False."""
+        access + diagonal), 'diag' (diagonal only) or False.  per_object=True predicts every
+        object with its own fit (`hyperparameters_per_object`, `nugget_per_object`); COV must then
+        be 'diag' or False."""
         hyp, nug = np.array(self.hyperparameters, dtype=float), float(self.nugget)
+        if per_object:
+            assert COV in ('diag', False), "per_object predictions provide the variance diagonal only"
+            hyp_b, nug_b = self.hyperparameters_per_object, self.nugget_per_object
         has_mean = self.substract_mean or self.Mean_Y is not None
         self.compute_kernel_matrix()
         self.inv_kernel_matrix = _LazyMatrices(self.N_sn, lambda i: self._object_matrices(i, hyp, nug)[1])
@@ -216,8 +221,8 @@ class Gaussian_process:
             self.new_binning = self.Time
             grid, goff = self._x_flat, self._off
             new_y0 = self._y0_flat if has_mean else None                   # :308-309
-            mean, var, info = self.batch.predict(hyp, nug, grid, goff=goff, new_y0=new_y0,
-                                                 want_var=want_var, flags=self.flags)
+            mean, var, info = self.batch.predict(hyp_b if per_object else hyp, nug_b if per_object else nug, grid,
+                                                 goff=goff, new_y0=new_y0, want_var=want_var, flags=self.flags)
             self._raise_if_bad(info)
             self.Prediction = RaggedView(mean, goff)
             self.prediction_variance = RaggedView(var, goff) if want_var else None
@@ -235,7 +240,8 @@ class Gaussian_process:
                     # no template: return_mean hands back y0 (per-epoch constant = diff) for any new_x;
                     # it only broadcasts in the reference when it is a scalar per object
                     new_y0 = np.repeat(self._diff_used[:, None], m, axis=1)
-            mean, var, info = self.batch.predict(hyp, nug, grid, new_y0=new_y0, want_var=want_var, flags=self.flags)
+            mean, var, info = self.batch.predict(hyp_b if per_object else hyp, nug_b if per_object else nug, grid,
+                                                 new_y0=new_y0, want_var=want_var, flags=self.flags)
             self._raise_if_bad(info)
             self.Prediction = list(mean)
             self.prediction_variance = list(var) if want_var else None

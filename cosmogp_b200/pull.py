@@ -16,7 +16,9 @@ class build_pull:
     def __init__(self, y, x, hyperparameters, nugget=0.,
                  y_err=None, y_mean=None, x_axis_mean=None,
                  kernel='RBF1D'):
-        """Same arguments and attributes as cosmogp/pull.py:10-40."""
+        """Same arguments and attributes as cosmogp/pull.py:10-40.  `hyperparameters` (and `nugget`) may
+        also be per-object arrays of shape (n_object, n_hyp) / (n_object,): each object is then
+        pulled with its own fit, as in the reference's per-object notebook loop."""
         self.y = y
         self.x = x
         self.hyperparameters = hyperparameters

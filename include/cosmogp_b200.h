@@ -86,6 +86,19 @@ int cgp_ll_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
                       const double* hyp_obj, const double* nugget_obj, double nugget, double floor, unsigned flags,
                       const int* order, int64_t n_active, double* ll_obj, int* info, void* stream);
 
+/* prediction and pulls with per-object hyperparameters (hyp_obj / nugget_obj indexed by object id):
+ * the rest of the reference's per-object loop (fit, predict, build_pull with each object's own fit). */
+int cgp_predict_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                           const double* x, const double* y, const double* y0, const double* y_err,
+                           const double* hyp_obj, const double* nugget_obj, double nugget, double floor, unsigned flags,
+                           const double* xnew, const int64_t* goff, int64_t m_shared,
+                           const double* new_y0, double* mean, double* var, int* info, void* stream);
+int cgp_loo_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                       const double* x, const double* y, const double* m, const double* y_err,
+                       const double* hyp_obj, const double* nugget_obj, double nugget, double floor, unsigned flags,
+                       int mode, double* pred, double* pred_var, double* pull, double* resid,
+                       int* info, void* stream);
+
 /* ---- prediction: replaces Gaussian_process.get_prediction + get_covariance_matrix
  *      (cosmogp/Gaussian_process.py:270-361).
  *      Grid: if goff == NULL the m_shared points of xnew are shared by all objects

@@ -58,3 +58,27 @@ def test_per_object_fits_match_reference_loop():
     i = 3
     ref = np.abs(fmin(lambda h: -O.log_likelihood(g["y"][i], g["x"][i], h[:2], h[2], g["y_err"][i]), [0.5, 2.0, 1.0], disp=False))
     assert_close(list(gn.hyperparameters_per_object[i]) + [gn.nugget_per_object[i]], ref, 5e-3, 5e-4)
+
+
+@pytest.mark.gpu
+def test_per_object_predict_and_pulls():
+    """Each object predicted / pulled with its own hyperparameters (cgp_predict_objhyp_dev,
+    cgp_loo_objhyp_dev), through the two-kernel route (>= 2048 objects) and the fused one."""
+    import cosmogp_b200 as cg
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(21)
+    for b in (2500, 40):
+        n = 30
+        x = np.sort(rng.uniform(0, 20, (b, n)), axis=1); y = rng.standard_normal((b, n)); ye = rng.uniform(0.1, 0.3, (b, n))
+        hyp = np.column_stack([rng.uniform(0.4, 1.2, b), rng.uniform(1.0, 4.0, b)]); nug = rng.uniform(0.0, 0.1, b)
+        gp = cg.gaussian_process_nobject(y, x, y_err=ye)
+        gp.hyperparameters_per_object, gp.nugget_per_object = hyp, nug
+        grid = np.linspace(-1, 21, 50)
+        gp.get_prediction(new_binning=grid, COV='diag', per_object=True)
+        bp = cg.build_pull(y, x, hyp, nugget=nug, y_err=ye)
+        bp.compute_pull(svd_method=False)
+        for i in (0, b // 2, b - 1):
+            mo, vo = O.predict(y[i], x[i], hyp[i], nug[i], grid, ye[i], full_cov=False)
+            assert_close(gp.Prediction[i], mo, 1e-9, 1e-12); assert_close(gp.prediction_variance[i], vo, 1e-9, 1e-13)
+            po = O.loo_closed_form(y[i], x[i], hyp[i], nug[i], ye[i])
+            assert_close(bp._pull[i], po[2], 1e-9, 1e-11)
