@@ -4,9 +4,9 @@
 //                     mode -> T_kk = L_kk^-1 (stored in place of the block) + log det
 //   panel           : L_ik = A_ik T_kk^T            (gemm_nt, in place)
 //   trailing update : A_ij -= L_ik L_jk^T, i >= j   (gemm_nt, lower tiles only)  <- N^3/3 of the work
-// gemm_nt is a 128x128x16 double-buffered (cp.async) FP64 tensor-core GEMM: 8 warps, each
-// 32x64 of C as 32 m8n8k4 DMMA accumulators; operands staged in shared memory with a
-// 20-double row pitch so the per-lane fragment loads are bank-conflict free.
+// gemm_nt is a 64x128x16 double-buffered (cp.async) FP64 tensor-core GEMM: 4 warps, each
+// 32x64 of C as 32 m8n8k4 DMMA accumulators, 3 CTAs per SM; operands staged in shared memory
+// with a 20-double row pitch so the per-lane fragment loads are bank-conflict free.
 // Reference path replaced: scipy.linalg.cholesky / inv / dot in cosmogp/inv_matrix.py:21-31 and
 // the H K^-1 products of cosmogp/Gaussian_process.py:332-361.
 #include "cgp_internal.h"
@@ -18,8 +18,11 @@
 namespace cgp {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, PITCH = BK + 4;   // PITCH % 16 == 4 -> conflict-free LDS.64
-constexpr int GEMM_THREADS = 256;
+// 64 x 128 tiles, 4 warps, 3 CTAs per SM: while one CTA is in its prologue (first cp.async latency) or
+// epilogue (C read-modify-write) the other two keep the DMMA pipe busy -- matters at K = 128, the
+// panel width of the blocked Cholesky (r01: 128x128 tiles with 1 CTA/SM gave 23 TFLOP/s there).
+constexpr int BM = 64, BN = 128, BK = 16, PITCH = BK + 4;   // PITCH % 16 == 4 -> conflict-free LDS.64
+constexpr int GEMM_THREADS = 128;
 constexpr size_t GEMM_SMEM = (size_t)2 * (BM + BN) * PITCH * sizeof(double);
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -33,22 +36,23 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
 
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 3)
 gemm_nt_kernel(const GemmArgs g) {
   extern __shared__ __align__(16) double sm[];
   double* As = sm;                                 // [2][BM][PITCH]
   double* Bs = sm + 2 * BM * PITCH;                // [2][BN][PITCH]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
-  const int wm = warp >> 1, wn = warp & 1;         // 4 x 2 warps: 32 x 64 of C each
+  const int wm = warp >> 1, wn = warp & 1;         // 2 x 2 warps: 32 x 64 of C each
 
-  int bi, bj;
-  if (g.lower_only) {                              // linear index -> (bi, bj), bi >= bj
-    const int t = blockIdx.x;
-    bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-    while (bi * (bi + 1) / 2 > t) --bi;
-    bj = t - bi * (bi + 1) / 2;
+  int bi, bj;                                      // bi: 64-row block, bj: 128-column block
+  if (g.lower_only) {                              // linear index -> (I, bj) with I >= bj, two 64-row halves each
+    const int t = blockIdx.x >> 1;
+    int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= t) ++I;
+    while (I * (I + 1) / 2 > t) --I;
+    bj = t - I * (I + 1) / 2;
+    bi = 2 * I + (blockIdx.x & 1);
   } else {
     const int nbn = g.n / BN;
     bi = blockIdx.x / nbn; bj = blockIdx.x - bi * nbn;
@@ -60,10 +64,15 @@ gemm_nt_kernel(const GemmArgs g) {
     double* as = As + st * BM * PITCH;
     double* bs = Bs + st * BN * PITCH;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = tid + i * GEMM_THREADS;        // 1024 16-byte pieces per operand
+    for (int i = 0; i < BM * 8 / GEMM_THREADS; ++i) {          // 16-byte pieces: 8 per row
+      const int p = tid + i * GEMM_THREADS;
       const int row = p >> 3, c2 = (p & 7) << 1;
       cp_async16(as + row * PITCH + c2, ga + (int64_t)row * g.lda + kc * BK + c2);
+    }
+#pragma unroll
+    for (int i = 0; i < BN * 8 / GEMM_THREADS; ++i) {
+      const int p = tid + i * GEMM_THREADS;
+      const int row = p >> 3, c2 = (p & 7) << 1;
       cp_async16(bs + row * PITCH + c2, gb + (int64_t)row * g.ldb + kc * BK + c2);
     }
     cp_async_commit();
@@ -307,7 +316,7 @@ __global__ void residual_kernel(const double* y, const double* y0, int64_t n, in
 
 // =========================================================================================
 int launch_gemm_nt(const GemmArgs& g, cudaStream_t stream) {
-  if (g.m % BM || g.n % BN || g.k % BK || g.m <= 0 || g.n <= 0 || g.k <= 0) return (int)cudaErrorInvalidValue;
+  if (g.m % 128 || g.n % BN || g.k % BK || g.m <= 0 || g.n <= 0 || g.k <= 0) return (int)cudaErrorInvalidValue;
   static bool init = false;
   if (!init) {
     cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
@@ -315,7 +324,8 @@ int launch_gemm_nt(const GemmArgs& g, cudaStream_t stream) {
     init = true;
   }
   const int64_t tm = g.m / BM, tn = g.n / BN;
-  const int64_t tiles = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  const int64_t t128 = g.m / 128;
+  const int64_t tiles = g.lower_only ? t128 * (t128 + 1) : tm * tn;       // two 64-row halves per 128x128 block
   gemm_nt_kernel<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM, stream>>>(g);
   count_launch();
   return (int)cudaGetLastError();
