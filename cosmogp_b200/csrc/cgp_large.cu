@@ -166,46 +166,67 @@ __global__ void cov_build_kernel(const CovArgs a) {
 
 // ---------------------------------------------------------------------------------------
 // Triangular solves against the blocked factor (diagonal blocks hold T = L_kk^-1).
-// w_k <- T_kk v_k  (or T_kk^T v_k): one CTA of 128 threads, one row each.
-__global__ void __launch_bounds__(128) diag_apply_kernel(const double* a, int64_t ld, int64_t k0, double* v, int trans) {
-  __shared__ double s[128];
-  const int i = threadIdx.x;
-  s[i] = v[k0 + i];
+// Fused sweep steps (one launch per 128-block instead of two): every CTA recomputes the small
+// triangular product of the step in shared memory (128 KB of T_kk from L2), CTA 0 publishes it, the
+// others apply it to their slice.  Input and output vectors are distinct, so there is no race on
+// the block being read.
+// forward step k: z_k = T_kk u_k -> zout;  u[row] -= L[row, k-block] z_k for rows below (in place).
+__global__ void __launch_bounds__(256) fwd_step_kernel(const double* a, int64_t ld, int64_t k0, int64_t n_pad,
+                                                       double* u, double* zout) {
+  __shared__ double sw[128], sz[128];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 128) sw[tid] = u[k0 + tid];
   __syncthreads();
   const double* t = a + k0 * ld + k0;
-  double acc = 0.0;
-  if (!trans) { for (int c = 0; c <= i; ++c) acc = fma(t[(int64_t)i * ld + c], s[c], acc); }
-  else { for (int c = i; c < 128; ++c) acc = fma(t[(int64_t)c * ld + i], s[c], acc); }
-  __syncthreads();
-  v[k0 + i] = acc;
-}
-// forward sweep: v[rows > k] -= L[rows, k-block] z_k.  One warp per row, 4 columns per lane.
-__global__ void __launch_bounds__(256) panel_gemv_sub_kernel(const double* a, int64_t ld, int64_t k0, int64_t n_pad, double* v) {
-  __shared__ double s[128];
-  if (threadIdx.x < 128) s[threadIdx.x] = v[k0 + threadIdx.x];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t row = k0 + 128 + (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= n_pad) return;
-  const double* p = a + row * ld + k0 + lane * 4;
-  const double2 u0 = *reinterpret_cast<const double2*>(p), u1 = *reinterpret_cast<const double2*>(p + 2);
-  double acc = u0.x * s[lane * 4] + u0.y * s[lane * 4 + 1] + u1.x * s[lane * 4 + 2] + u1.y * s[lane * 4 + 3];
+  for (int r = warp * 16; r < warp * 16 + 16; ++r) {              // 8 warps x 16 rows, 4 columns per lane
+    const double* p = t + (int64_t)r * ld + lane * 4;
+    const double2 q0 = *reinterpret_cast<const double2*>(p), q1 = *reinterpret_cast<const double2*>(p + 2);
+    double acc = q0.x * sw[lane * 4] + q0.y * sw[lane * 4 + 1] + q1.x * sw[lane * 4 + 2] + q1.y * sw[lane * 4 + 3];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) v[row] -= acc;
-}
-// backward sweep: v[cols < k] -= L[k-block, cols]^T alpha_k.  One thread per column.
-__global__ void __launch_bounds__(128) panel_gemvT_sub_kernel(const double* a, int64_t ld, int64_t k0, double* v) {
-  __shared__ double s[128];
-  s[threadIdx.x] = v[k0 + threadIdx.x];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sz[r] = acc;
+  }
   __syncthreads();
-  const int64_t col = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (col >= k0) return;
-  const double* p = a + k0 * ld + col;
+  if (blockIdx.x == 0) { if (tid < 128) zout[k0 + tid] = sz[tid]; return; }
+  const int64_t row0 = k0 + 128 + (int64_t)(blockIdx.x - 1) * 64;
+  for (int rr = warp * 8; rr < warp * 8 + 8; ++rr) {               // 64 rows per CTA
+    const int64_t row = row0 + rr;
+    if (row >= n_pad) break;
+    const double* p = a + row * ld + k0 + lane * 4;
+    const double2 q0 = *reinterpret_cast<const double2*>(p), q1 = *reinterpret_cast<const double2*>(p + 2);
+    double acc = q0.x * sz[lane * 4] + q0.y * sz[lane * 4 + 1] + q1.x * sz[lane * 4 + 2] + q1.y * sz[lane * 4 + 3];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) u[row] -= acc;
+  }
+}
+// backward step k: alpha_k = T_kk^T z_k -> aout;  z[col] -= L[k-block, col]^T alpha_k for cols left of k (in place).
+__global__ void __launch_bounds__(256) bwd_step_kernel(const double* a, int64_t ld, int64_t k0, double* z, double* aout) {
+  __shared__ double sw[128], sa[128], part[256];
+  const int tid = threadIdx.x;
+  if (tid < 128) sw[tid] = z[k0 + tid];
+  __syncthreads();
+  const double* t = a + k0 * ld + k0;
+  {                                                                 // column c = tid % 128, rows split in two halves
+    const int c = tid & 127, h = tid >> 7;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int r = h * 64; r < h * 64 + 64; ++r) acc = fma(t[(int64_t)r * ld + c], sw[r], acc);
+    part[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < 128) sa[tid] = part[tid] + part[tid + 128];
+  __syncthreads();
+  if (blockIdx.x == 0) { if (tid < 128) aout[k0 + tid] = sa[tid]; return; }
+  const int64_t col = (int64_t)(blockIdx.x - 1) * 128 + (tid & 127);
+  const int h = tid >> 7;
+  const double* p = a + (k0 + h * 64) * ld + col;
   double acc = 0.0;
 #pragma unroll 8
-  for (int r = 0; r < 128; ++r) acc = fma(p[(int64_t)r * ld], s[r], acc);
-  v[col] -= acc;
+  for (int r = 0; r < 64; ++r) acc = fma(p[(int64_t)r * ld], sa[h * 64 + r], acc);
+  part[tid] = acc;
+  __syncthreads();
+  if (tid < 128) z[col] -= part[tid] + part[tid + 128];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -375,7 +396,19 @@ int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* i
   potrf_setup_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(blk_off, blk_aoff, nblk, ld);
   count_launch();
   int rc = 0;
-  for (int k = 0; k < nblk; ++k) {
+  // Look-ahead: the diagonal block and panel of column k+1 (one CTA + a skinny GEMM, latency bound)
+  // run on a high-priority side stream while the main stream applies panel k to the rest of the
+  // trailing matrix; only the 128 columns of block k+1 are updated first.
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
+  if (!side) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return (int)cudaGetLastError();
+    cudaEventCreateWithFlags(&ev_col, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming);
+  }
+  auto factor_panel = [&](int k, cudaStream_t s_) -> int {      // diag block k -> T_kk, then L_ik = A_ik T_kk^T
     const int64_t k0 = (int64_t)k * 128;
     SmallArgs s; memset(&s, 0, sizeof s);
     s.n_obj = 1; s.off = blk_off;                  // {0, 128}
@@ -383,21 +416,39 @@ int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* i
     s.moff = blk_aoff + k; s.mld = ld; s.linv = a;
     s.logdet = logdet_blocks + k; s.info = info_blocks + k;
     s.cov.amp_auto = 1.0; s.cov.amp_cross = 1.0;
-    int e = launch_small(TASK_MATRICES, 1, 128, s, st);
-    if (e) { rc = e; break; }
+    int e = launch_small(TASK_MATRICES, 1, 128, s, s_);
+    if (e) return e;
     const int64_t rest = n_pad - k0 - 128;
-    if (rest <= 0) break;
-    GemmArgs p;                                      // panel: L_ik = A_ik T_kk^T (in place, one tile column)
+    if (rest <= 0) return 0;
+    GemmArgs p;                                      // in place, one tile column
     p.a = a + (k0 + 128) * ld + k0; p.lda = ld;
     p.b = a + k0 * ld + k0; p.ldb = ld;
     p.c = a + (k0 + 128) * ld + k0; p.ldc = ld;
     p.m = (int)rest; p.n = 128; p.k = 128; p.alpha = 1.0; p.beta = 0.0; p.lower_only = 0;
-    if ((e = launch_gemm_nt(p, st))) { rc = e; break; }
-    GemmArgs u;                                      // trailing update on the lower triangle
-    u.a = p.c; u.lda = ld; u.b = p.c; u.ldb = ld;
-    u.c = a + (k0 + 128) * ld + (k0 + 128); u.ldc = ld;
-    u.m = (int)rest; u.n = (int)rest; u.k = 128; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
-    if ((e = launch_gemm_nt(u, st))) { rc = e; break; }
+    return launch_gemm_nt(p, s_);
+  };
+  rc = factor_panel(0, st);
+  for (int k = 0; k + 1 < nblk && !rc; ++k) {
+    const int64_t k0 = (int64_t)k * 128;
+    const int64_t rest = n_pad - k0 - 128;           // rows below block k
+    const double* panel = a + (k0 + 128) * ld + k0;  // L[k+1:, k]
+    GemmArgs c;                                      // block column k+1 first (includes its diagonal block)
+    c.a = panel; c.lda = ld; c.b = panel; c.ldb = ld;
+    c.c = a + (k0 + 128) * ld + (k0 + 128); c.ldc = ld;
+    c.m = (int)rest; c.n = 128; c.k = 128; c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0;
+    if ((rc = launch_gemm_nt(c, st))) break;
+    cudaEventRecord(ev_col, st);
+    cudaStreamWaitEvent(side, ev_col, 0);
+    if ((rc = factor_panel(k + 1, side))) break;
+    cudaEventRecord(ev_panel, side);
+    if (rest > 128) {                                // the rest of the trailing matrix, lower triangle
+      GemmArgs u;
+      u.a = panel + 128 * ld; u.lda = ld; u.b = u.a; u.ldb = ld;
+      u.c = a + (k0 + 256) * ld + (k0 + 256); u.ldc = ld;
+      u.m = (int)(rest - 128); u.n = (int)(rest - 128); u.k = 128; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+      if ((rc = launch_gemm_nt(u, st))) break;
+    }
+    cudaStreamWaitEvent(st, ev_panel, 0);
   }
   potrf_finish_kernel<<<1, 32, 0, st>>>(logdet_blocks, info_blocks, nblk, logdet_out, info_out);
   count_launch();
@@ -406,28 +457,39 @@ int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* i
 }
 
 // v <- L^-1 v (forward) then, if backward, v <- L^-T v.  z_out (optional) receives L^-1 v.
+// One fused launch per 128-block and direction; a stream-ordered scratch vector holds z.
 int large_potrs(const double* a, int64_t n_pad, int64_t ld, double* v, double* z_out, int backward, cudaStream_t st) {
   const int nblk = (int)(n_pad / 128);
+  double* z = nullptr;
+  cudaError_t ce = cudaMallocAsync((void**)&z, n_pad * sizeof(double), st);
+  if (ce != cudaSuccess) return (int)ce;
   for (int k = 0; k < nblk; ++k) {
     const int64_t k0 = (int64_t)k * 128;
-    diag_apply_kernel<<<1, 128, 0, st>>>(a, ld, k0, v, 0);
     const int64_t rest = n_pad - k0 - 128;
-    if (rest > 0) panel_gemv_sub_kernel<<<(unsigned)((rest + 7) / 8), 256, 0, st>>>(a, ld, k0, n_pad, v);
-    count_launch(rest > 0 ? 2 : 1);
+    fwd_step_kernel<<<(unsigned)(1 + (rest + 63) / 64), 256, 0, st>>>(a, ld, k0, n_pad, v, z);
   }
-  if (z_out) cudaMemcpyAsync(z_out, v, n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st);
-  if (backward) return large_potrs_backward(a, n_pad, ld, v, st);
+  count_launch(nblk);
+  if (z_out) cudaMemcpyAsync(z_out, z, n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  if (backward) {
+    for (int k = nblk - 1; k >= 0; --k) bwd_step_kernel<<<(unsigned)(1 + k), 256, 0, st>>>(a, ld, (int64_t)k * 128, z, v);
+    count_launch(nblk);
+  } else {
+    cudaMemcpyAsync(v, z, n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  }
+  cudaFreeAsync(z, st);
   return (int)cudaGetLastError();
 }
 
+// alpha = L^-T z for a vector z that already holds L^-1 r (in place).
 int large_potrs_backward(const double* a, int64_t n_pad, int64_t ld, double* v, cudaStream_t st) {
   const int nblk = (int)(n_pad / 128);
-  for (int k = nblk - 1; k >= 0; --k) {
-    const int64_t k0 = (int64_t)k * 128;
-    diag_apply_kernel<<<1, 128, 0, st>>>(a, ld, k0, v, 1);
-    if (k0 > 0) panel_gemvT_sub_kernel<<<(unsigned)(k0 / 128), 128, 0, st>>>(a, ld, k0, v);
-    count_launch(k0 > 0 ? 2 : 1);
-  }
+  double* z = nullptr;
+  cudaError_t ce = cudaMallocAsync((void**)&z, n_pad * sizeof(double), st);
+  if (ce != cudaSuccess) return (int)ce;
+  cudaMemcpyAsync(z, v, n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  for (int k = nblk - 1; k >= 0; --k) bwd_step_kernel<<<(unsigned)(1 + k), 256, 0, st>>>(a, ld, (int64_t)k * 128, z, v);
+  count_launch(nblk);
+  cudaFreeAsync(z, st);
   return (int)cudaGetLastError();
 }
 
