@@ -364,3 +364,40 @@ def test_factor_once_predict_many(L):
     fs = small.factor_dev(hyp, nug)
     mf, vf, _ = small.predict_factored_dev(fs, torch.from_numpy(grid).cuda(), None, None, True)
     assert_close(mf.cpu().numpy().reshape(5, 500), ms, 1e-13, 1e-13); assert_close(vf.cpu().numpy().reshape(5, 500), vs, 1e-13, 1e-14)
+
+
+def test_degenerate_inputs(L):
+    """Empty batches, empty grids, NaN / singular hyperparameters: defined outputs, no crash."""
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(0, 10, 20)); y = rng.standard_normal(20); ye = np.full(20, 0.2)
+    # no objects at all
+    off0 = np.zeros(1, dtype=np.int64); tot_c = C.c_double(7.0)
+    hyp = np.array([1.0, 1.0])
+    rc = L.lib().cgp_ll_batched_host(0, L.hptr(off0), 1, None, None, None, None, L.hptr(hyp), 0.0, 0.0, 0, None, None, C.byref(tot_c))
+    assert rc == 0 and tot_c.value == 0.0
+    # empty grid
+    mean, var, info = run_predict(L, [x], [y], None, [ye], [1.0, 2.0], 0.0, np.zeros(0))
+    assert mean.shape == (1, 0) and info[0] == 0
+    # NaN hyperparameter: every pivot is NaN -> reported as not positive definite, outputs NaN
+    ll, info, tot, rc = run_ll(L, [x], [y], None, [ye], [np.nan, 2.0], 0.0)
+    assert rc == 1 and info[0] == 1 and np.isnan(ll[0])
+    # 2D metric that is not positive definite (l_x^2 l_y^2 - l_xy^2 < 0): scipy gives NaN distances
+    x2 = rng.uniform(0, 10, (12, 2))
+    off = np.array([0, 12], dtype=np.int64); ll2 = np.zeros(1); inf2 = np.zeros(1, dtype=np.int32); t2 = C.c_double(0)
+    h2 = np.array([1.0, 1.0, 1.0, 5.0])
+    rc = L.lib().cgp_ll_batched_host(1, L.hptr(off), 2, L.hptr(np.ascontiguousarray(x2)), L.hptr(np.ascontiguousarray(y[:12])), None,
+                                     L.hptr(np.ascontiguousarray(ye[:12])), L.hptr(h2), 0.0, 0.0, 0, L.hptr(ll2), L.hptr(inf2), C.byref(t2))
+    assert rc >= 0                                                          # must not crash; the value is garbage-in
+    # huge length scale: K is numerically singular without noise -> flagged; with noise -> finite and equal to the oracle
+    ll, info, _, rc = run_ll(L, [x], [y], None, [ye], [1.0, 1e6], 0.0)
+    assert info[0] == 0
+    assert_close(ll[0], O.log_likelihood(y, x, [1.0, 1e6], 0.0, ye), 1e-7)
+    # bad dim / NULL pointers are argument errors, not crashes
+    rc = L.lib().cgp_ll_batched_host(1, L.hptr(off), 3, L.hptr(x), L.hptr(y), None, None, L.hptr(hyp), 0.0, 0.0, 0, L.hptr(ll2), L.hptr(inf2), None)
+    assert rc < 0 and b"dim" in L.lib().cgp_last_error()
+    rc = L.lib().cgp_ll_batched_host(1, L.hptr(off), 1, None, L.hptr(y), None, None, L.hptr(hyp), 0.0, 0.0, 0, L.hptr(ll2), L.hptr(inf2), None)
+    assert rc < 0
+    # object too large for the shared-memory path: explicit size error
+    big = np.zeros(300); offb = np.array([0, 300], dtype=np.int64)
+    rc = L.lib().cgp_ll_batched_host(1, L.hptr(offb), 1, L.hptr(big), L.hptr(big), None, None, L.hptr(hyp), 0.0, 0.0, 0, L.hptr(ll2), L.hptr(inf2), None)
+    assert rc == -2 and b"exceeds" in L.lib().cgp_last_error()
