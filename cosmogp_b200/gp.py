@@ -106,6 +106,24 @@ class Gaussian_process:
                                       y_err=self._ye_flat, dim=self._dim)
         return self._batch
 
+    @property
+    def _is_large(self):
+        """Objects beyond the shared-memory path (N > 224) go one by one through the HBM-resident
+        blocked factorisation (cosmogp_b200.dense.LargeObject)."""
+        return len(self._off) > 1 and int(np.diff(self._off).max()) > _lib.CGP_SMALL_MAX_N
+
+    def _large_objects(self):
+        if getattr(self, "_large", None) is None:
+            from .dense import LargeObject
+            self._large = []
+            for i in range(self.N_sn):
+                o0, o1 = self._off[i], self._off[i + 1]
+                self._large.append(LargeObject(
+                    self._x_flat[o0:o1], self._y_flat[o0:o1],
+                    None if self._ye_flat is None else self._ye_flat[o0:o1],
+                    None if self._y0_flat is None else self._y0_flat[o0:o1], dim=self._dim, flags=self.flags))
+        return self._large
+
     @staticmethod
     def _raise_if_bad(info):
         bad = np.nonzero(info)[0]
@@ -123,6 +141,11 @@ class Gaussian_process:
         else:
             Nugget = self.nugget
             hyperparameter = Hyperparameter
+        if self._is_large:
+            per_object = np.array([o.factor(hyperparameter, Nugget) for o in self._large_objects()])
+            self.log_likelihood_per_object = per_object
+            self.log_likelihood = np.array([float(np.add.accumulate(per_object)[-1])])
+            return
         total, per_object, info = self.batch.log_likelihood(hyperparameter, Nugget, flags=self.flags)
         self._raise_if_bad(info)
         self.log_likelihood_per_object = per_object
@@ -215,6 +238,30 @@ class Gaussian_process:
         self.compute_kernel_matrix()
         self.inv_kernel_matrix = _LazyMatrices(self.N_sn, lambda i: self._object_matrices(i, hyp, nug)[1])
         want_var = bool(COV)
+
+        if self._is_large:
+            assert not per_object, "per-object hyperparameters are not wired for large objects"
+            self.as_the_same_time = new_binning is None
+            self.new_binning = self.Time if new_binning is None else new_binning
+            self.Prediction, self.prediction_variance = [], ([] if want_var else None)
+            for i, obj in enumerate(self._large_objects()):
+                o0, o1 = self._off[i], self._off[i + 1]
+                obj.factor(hyp, nug)
+                if new_binning is None:
+                    grid, ny0 = self._x_flat[o0:o1], (self._y0_flat[o0:o1] if has_mean else None)
+                else:
+                    grid = np.ascontiguousarray(new_binning, dtype=np.float64)
+                    ny0 = None
+                    if has_mean:
+                        tmpl = _mean.template_on_grid(grid, self._dim, self.Mean_Y, self.Time_mean)
+                        ny0 = (tmpl if tmpl is not None else 0.0) + self._diff_used[i] * np.ones(len(grid))
+                m, v = obj.predict(grid, new_y0=ny0, want_var=want_var)
+                self.Prediction.append(m)
+                if want_var:
+                    self.prediction_variance.append(v)
+            if COV is True:
+                self.get_covariance_matrix()
+            return
 
         if new_binning is None:
             self.as_the_same_time = True

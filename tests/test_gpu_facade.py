@@ -159,3 +159,34 @@ def test_streamed_evaluator_matches_resident_batch(cg):
     assert not info.any() and tot == t2
     assert np.array_equal(ll, ll2) and np.array_equal(mean, m2) and np.array_equal(var, v2)
     assert ev.h2d_bytes == b * (4 * n + m) * 8 and ev.d2h_bytes == b * (8 + 16 * m + 4)
+
+
+def test_large_objects_through_the_facade(cg):
+    """Objects beyond the shared-memory path (N > 224) are routed to the blocked HBM factorisation."""
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(8)
+    n = 400
+    x = rng.uniform(-100, 100, (n, 2)); ye = rng.uniform(0.15, 0.3, n)
+    y = np.cos(x[:, 0] / 40) + 0.2 * rng.standard_normal(n)
+    hyp, nug = [1.0, 30.0, 25.0, 50.0], 0.05
+    gp = cg.gaussian_process(y, x, kernel="RBF2D", y_err=ye)
+    gp.compute_log_likelihood(hyp, svd_method=False)
+    gp.nugget = nug
+    gp.compute_log_likelihood(hyp, svd_method=False)
+    assert_close(gp.log_likelihood[0], O.log_likelihood(y, x, hyp, nug, ye, kind="2d"), 1e-9)
+    grid = rng.uniform(-100, 100, (150, 2))
+    gp.hyperparameters = np.array(hyp)
+    gp.get_prediction(new_binning=grid, COV='diag')
+    mo, vo = O.predict(y, x, hyp, nug, grid, ye, kind="2d", full_cov=False)
+    assert_close(gp.Prediction[0], mo, 1e-9, 1e-11); assert_close(gp.prediction_variance[0], vo, 1e-9, 1e-12)
+    # 1D, with a mean template, own-epoch prediction
+    n1 = 300
+    x1 = np.sort(rng.uniform(0, 100, n1)); ye1 = np.full(n1, 0.2)
+    tm = np.linspace(-5, 105, 40); ym = np.sin(tm / 15)
+    y1 = np.sin(x1 / 15) + 0.3 + 0.2 * rng.standard_normal(n1)
+    g1 = cg.gaussian_process(y1, x1, y_err=ye1, Mean_Y=ym, Time_mean=tm)
+    g1.hyperparameters = np.array([0.5, 3.0]); g1.nugget = 0.0
+    g1.get_prediction(COV='diag')
+    y0 = O.return_mean_1d(y1, x1, ym, tm)
+    mo, vo = O.predict(y1, x1, [0.5, 3.0], 0.0, x1, ye1, y0, y0, full_cov=False)
+    assert_close(g1.Prediction[0], mo, 1e-9, 1e-11); assert_close(g1.prediction_variance[0], vo, 1e-9, 1e-12)
