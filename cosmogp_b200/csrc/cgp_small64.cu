@@ -109,9 +109,10 @@ static unsigned long long* next_ticket(cudaStream_t stream) {
 constexpr int n_vec64(int task) { return task == TASK_LOO ? 6 : 1; }
 
 // Registers are allocated per SM sub-partition (16 K each): 3 warps per partition need <= 168
-// registers per thread, hence the minimum-blocks bound (shared memory then allows 11 per SM).
+// registers per thread (grid phase: 64 accumulators + 32 fragments), 4 warps <= 128 (factorisation,
+// pulls: shared memory allows 16+ objects per SM below 56 points); hence the minimum-blocks bounds.
 template <int DIM, int TASK, int NB>
-__global__ void __launch_bounds__(32, 12)
+__global__ void __launch_bounds__(32, (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) ? 12 : 16)
 gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
