@@ -97,6 +97,40 @@ class Gaussian_process:
 
         self.as_the_same_time = True
         self._batch = None
+        self._dist = False              # True for objects made by `sharded()`: likelihoods are all-reduced
+
+    @classmethod
+    def sharded(cls, y, Time, kernel='RBF1D', y_err=None, diff=None, Mean_Y=None, Time_mean=None,
+                substract_mean=False, rank=None, world=None):
+        """One process per GPU (torch.distributed): every rank passes the FULL lists and keeps the
+        contiguous range of objects `local_range`, balanced by sum N^3 (cosmogp_b200.sharding).  Objects
+        are independent, so the only exchange is one all-reduced double per likelihood evaluation
+        (summed in rank order: identical on every rank); `find_hyperparameters` therefore returns the
+        same optimum everywhere and `get_prediction` fills the local objects (`gather` collects them)."""
+        from . import sharding
+        sizes = [len(v) for v in y]
+        a, b = sharding.my_range(sizes, rank, world)
+        cut = lambda v: None if v is None else v[a:b]
+        obj = cls(y[a:b], Time[a:b], kernel=kernel, y_err=cut(y_err), diff=cut(diff), Mean_Y=Mean_Y,
+                  Time_mean=Time_mean, substract_mean=substract_mean)
+        sigma, L = init_rbf(Time, y)                     # the global initial guess (quirk Q6 uses the LAST object)
+        obj.hyperparameters = np.array([sigma, L]) if obj._dim == 1 else np.array([sigma, L, L, 0.])
+        obj._dist, obj.local_range, obj.N_total, obj._all_sizes = True, (a, b), len(y), sizes
+        return obj
+
+    def gather(self, per_object_arrays):
+        """All ranks' per-object arrays (e.g. `Prediction`) concatenated in object order, on every rank."""
+        from . import sharding
+        flat = np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in per_object_arrays]) if len(per_object_arrays) else np.zeros(0)
+        per = [len(np.asarray(v).ravel()) for v in per_object_arrays]
+        import torch.distributed as dist
+        if not (self._dist and dist.is_initialized() and dist.get_world_size() > 1):
+            return list(per_object_arrays)
+        width = per[0] if per else 0                      # equal-length outputs (shared grid)
+        ranges = sharding.balanced_ranges(self._all_sizes, dist.get_world_size())
+        counts = [(r[1] - r[0]) * width for r in ranges]
+        allflat = sharding.gather_ragged(flat, counts, device=self.batch.device)
+        return list(allflat.reshape(-1, width)) if width else []
 
     # ------------------------------------------------------------------ device state
     @property
@@ -147,6 +181,12 @@ class Gaussian_process:
             self.log_likelihood = np.array([float(np.add.accumulate(per_object)[-1])])
             return
         total, per_object, info = self.batch.log_likelihood(hyperparameter, Nugget, flags=self.flags)
+        if self._dist:
+            from . import sharding
+            bad = sharding.allreduce_sum(float(np.count_nonzero(info)), device=self.batch.device)
+            if bad:
+                raise np.linalg.LinAlgError("%d object(s) with a covariance that is not positive definite" % int(bad))
+            total = sharding.allreduce_sum(total, device=self.batch.device)
         self._raise_if_bad(info)
         self.log_likelihood_per_object = per_object
         self.log_likelihood = np.array([total])             # shape (1,), quirk Q5
