@@ -399,15 +399,23 @@ int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* i
   // Look-ahead: the diagonal block and panel of column k+1 (one CTA + a skinny GEMM, latency bound)
   // run on a high-priority side stream while the main stream applies panel k to the rest of the
   // trailing matrix; only the 128 columns of block k+1 are updated first.
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
-  if (!side) {
+  constexpr int MAX_DEV = 16;
+  static cudaStream_t sides[MAX_DEV] = {nullptr};          // per device of this process
+  static cudaEvent_t evs[MAX_DEV][2] = {{nullptr, nullptr}};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) { cudaFreeAsync(scratch, st); return (int)cudaErrorInvalidDevice; }
+  if (!sides[dev]) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return (int)cudaGetLastError();
-    cudaEventCreateWithFlags(&ev_col, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming);
+    if (cudaStreamCreateWithPriority(&sides[dev], cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaFreeAsync(scratch, st);
+      return (int)cudaGetLastError();
+    }
+    cudaEventCreateWithFlags(&evs[dev][0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&evs[dev][1], cudaEventDisableTiming);
   }
+  cudaStream_t side = sides[dev];
+  cudaEvent_t ev_col = evs[dev][0], ev_panel = evs[dev][1];
   auto factor_panel = [&](int k, cudaStream_t s_) -> int {      // diag block k -> T_kk, then L_ik = A_ik T_kk^T
     const int64_t k0 = (int64_t)k * 128;
     SmallArgs s; memset(&s, 0, sizeof s);

@@ -97,11 +97,14 @@ __device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
 
 // Ring of work counters (one per launch in flight), zeroed in stream order before each launch.
 static unsigned long long* next_ticket(cudaStream_t stream) {
-  static unsigned long long* ring = nullptr;
-  static unsigned idx = 0;
   constexpr unsigned RING = 256;
-  if (!ring && cudaMalloc((void**)&ring, RING * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
-  unsigned long long* t = ring + (idx++ % RING);
+  constexpr int MAX_DEV = 16;
+  static unsigned long long* ring[MAX_DEV] = {nullptr};   // one ring per device of this process
+  static unsigned idx[MAX_DEV] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+  if (!ring[dev] && cudaMalloc((void**)&ring[dev], RING * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+  unsigned long long* t = ring[dev] + (idx[dev]++ % RING);
   if (cudaMemsetAsync(t, 0, sizeof(unsigned long long), stream) != cudaSuccess) return nullptr;
   return t;
 }
