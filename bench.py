@@ -255,9 +255,9 @@ def main():
 
     # ---- end to end through the numpy-in/numpy-out layer: every step uploads the step's inputs from
     # pinned host memory, runs LL + predict and downloads ll/mean/var; chunks of objects are
-    # pipelined over 3 streams so PCIe (both directions) overlaps the kernels
+    # pipelined over 4 streams so PCIe (both directions) overlaps the kernels
     from cosmogp_b200.batch import StreamedEvaluator
-    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=10, n_streams=3)
+    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "16")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "4")))
     for name, arr in (("x", x), ("y", y), ("y0", y0.reshape(B, N_EPOCH)), ("y_err", ye), ("new_y0", ny0)):
         ev_e2e.host(name)[...] = arr
 
