@@ -1,6 +1,6 @@
 """Timings of the BASELINE configs other than the bench.py workload: C1 (single curve, N=50,
 M=500) and C5 (leave-one-out pulls, N=40) on one B200, with the CPU port beside them.
-   python tools/bench_configs.py [--c5 1000000]"""
+   python tests/perf_configs.py [--c5 1000000]"""
 import argparse, json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
