@@ -90,8 +90,11 @@ __device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
     a0 = fma(-lg, lc0, a0); a1 = fma(-lg, lc1, a1);
     const double tk0 = __shfl_sync(FULL, t0, k * 4 + L.t) * rinv;
     const double tk1 = __shfl_sync(FULL, t1, k * 4 + L.t) * rinv;
-    if (L.g == k) { t0 = tk0; t1 = tk1; }
-    else if (L.g > k) { t0 = fma(-lg, tk0, t0); t1 = fma(-lg, tk1, t1); }
+    // branch-free row operation on T: rows above k keep their value (coefficient 0), row k takes the
+    // scaled pivot row (ncu r01f: the branchy form cost 544 register moves per object)
+    const double f = (L.g > k) ? lg : 0.0;
+    const double n0 = fma(-f, tk0, t0), n1 = fma(-f, tk1, t1);
+    t0 = (L.g == k) ? tk0 : n0; t1 = (L.g == k) ? tk1 : n1;
   }
 }
 
