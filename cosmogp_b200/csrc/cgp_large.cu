@@ -396,9 +396,9 @@ int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* i
   potrf_setup_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(blk_off, blk_aoff, nblk, ld);
   count_launch();
   int rc = 0;
-  // Look-ahead: the diagonal block and panel of column k+1 (one CTA + a skinny GEMM, latency bound)
-  // run on a high-priority side stream while the main stream applies panel k to the rest of the
-  // trailing matrix; only the 128 columns of block k+1 are updated first.
+  // Look-ahead: the diagonal blocks and panels of the NEXT pair of block columns (two CTAs + skinny
+  // GEMMs, latency bound) run on a high-priority side stream while the main stream applies the
+  // current pair to the rest of the trailing matrix; only the next pair's columns are updated first.
   constexpr int MAX_DEV = 16;
   static cudaStream_t sides[MAX_DEV] = {nullptr};          // per device of this process
   static cudaEvent_t evs[MAX_DEV][2] = {{nullptr, nullptr}};
@@ -435,25 +435,47 @@ int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* i
     p.m = (int)rest; p.n = 128; p.k = 128; p.alpha = 1.0; p.beta = 0.0; p.lower_only = 0;
     return launch_gemm_nt(p, s_);
   };
-  rc = factor_panel(0, st);
-  for (int k = 0; k + 1 < nblk && !rc; ++k) {
+  // Two block columns form one 256-wide pair: the trailing update then runs with K = 256 (one pass
+  // over C for two panels, and a deeper K loop per tile).
+  auto factor_pair = [&](int p, cudaStream_t s_) -> int {
+    const int k = 2 * p;
+    int e = factor_panel(k, s_);
+    if (e || k + 1 >= nblk) return e;
     const int64_t k0 = (int64_t)k * 128;
-    const int64_t rest = n_pad - k0 - 128;           // rows below block k
-    const double* panel = a + (k0 + 128) * ld + k0;  // L[k+1:, k]
-    GemmArgs c;                                      // block column k+1 first (includes its diagonal block)
+    const double* panel = a + (k0 + 128) * ld + k0;            // L[k+1:, k]
+    GemmArgs c;                                                // block column k+1 (with its diagonal block)
     c.a = panel; c.lda = ld; c.b = panel; c.ldb = ld;
     c.c = a + (k0 + 128) * ld + (k0 + 128); c.ldc = ld;
-    c.m = (int)rest; c.n = 128; c.k = 128; c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0;
+    c.m = (int)(n_pad - k0 - 128); c.n = 128; c.k = 128; c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0;
+    if ((e = launch_gemm_nt(c, s_))) return e;
+    return factor_panel(k + 1, s_);
+  };
+  const int npair = (nblk + 1) / 2;
+  rc = factor_pair(0, st);
+  for (int p = 0; p + 1 < npair && !rc; ++p) {
+    const int64_t k0 = (int64_t)p * 256;
+    const int64_t rest = n_pad - k0 - 256;             // rows below the pair
+    const double* w = a + (k0 + 256) * ld + k0;        // L[2p+2:, 2p..2p+1], K = 256 contiguous
+    GemmArgs c;                                        // the next pair's block columns first
+    c.a = w; c.lda = ld; c.b = w; c.ldb = ld;
+    c.c = a + (k0 + 256) * ld + (k0 + 256); c.ldc = ld;
+    c.m = (int)rest; c.n = 128; c.k = 256; c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0;
     if ((rc = launch_gemm_nt(c, st))) break;
+    if (rest > 128) {
+      c.a = w + 128 * ld; c.b = w + 128 * ld;
+      c.c = a + (k0 + 384) * ld + (k0 + 384);
+      c.m = (int)(rest - 128);
+      if ((rc = launch_gemm_nt(c, st))) break;
+    }
     cudaEventRecord(ev_col, st);
     cudaStreamWaitEvent(side, ev_col, 0);
-    if ((rc = factor_panel(k + 1, side))) break;
+    if ((rc = factor_pair(p + 1, side))) break;
     cudaEventRecord(ev_panel, side);
-    if (rest > 128) {                                // the rest of the trailing matrix, lower triangle
+    if (rest > 256) {                                  // the rest of the trailing matrix, lower triangle
       GemmArgs u;
-      u.a = panel + 128 * ld; u.lda = ld; u.b = u.a; u.ldb = ld;
-      u.c = a + (k0 + 256) * ld + (k0 + 256); u.ldc = ld;
-      u.m = (int)(rest - 128); u.n = (int)(rest - 128); u.k = 128; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
+      u.a = w + 256 * ld; u.lda = ld; u.b = u.a; u.ldb = ld;
+      u.c = a + (k0 + 512) * ld + (k0 + 512); u.ldc = ld;
+      u.m = (int)(rest - 256); u.n = (int)(rest - 256); u.k = 256; u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1;
       if ((rc = launch_gemm_nt(u, st))) break;
     }
     cudaStreamWaitEvent(st, ev_panel, 0);
