@@ -184,6 +184,33 @@ class DeviceBatch:
         torch.cuda.current_stream(self.device).synchronize()
         return c["ll_h"].numpy()[:k].copy(), c["info_h"].numpy()[:k].copy()
 
+    def fit_objects(self, start, nugget=0.0, floor=0.0, flags=0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfun=None):
+        """One Nelder-Mead fit per object, entirely on the device (cgp_fit_objects_dev).
+        start: (n_obj, nh) or (n_obj, nh+1) -- with nh+1 columns the last one is the object's nugget.
+        -> (par (n_obj, n_par), nll (n_obj,), iterations, evaluations) host arrays; the decisions are
+        scipy.optimize.fmin's, object by object (same results as fit.nelder_mead_lockstep)."""
+        start = np.ascontiguousarray(start, dtype=np.float64)
+        assert start.ndim == 2 and start.shape[0] == self.n_obj
+        n_par = start.shape[1]
+        maxiter = n_par * 200 if maxiter is None else int(maxiter)
+        maxfun = n_par * 200 if maxfun is None else int(maxfun)
+        b = max(self.n_obj, 1)
+        x0 = self._up(start)
+        par = torch.empty((b, n_par), dtype=torch.float64, device=self.device)
+        nll = torch.empty(b, dtype=torch.float64, device=self.device)
+        its = torch.empty(b, dtype=torch.int32, device=self.device)
+        calls = torch.empty(b, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_fit_objects_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                                self._p(self.y), self._p(self.y0), self._p(self.y_err), self._p(x0), n_par,
+                                                float(nugget), float(floor), int(flags), float(xatol), float(fatol),
+                                                maxiter, maxfun, self._p(par), self._p(nll), self._p(its), self._p(calls),
+                                                self._stream())
+        _lib.check(rc, "cgp_fit_objects_dev")
+        k = self.n_obj
+        return (par[:k].cpu().numpy(), nll[:k].cpu().numpy(), its[:k].cpu().numpy().astype(np.int64),
+                calls[:k].cpu().numpy().astype(np.int64))
+
     def _objhyp(self, hyp, nugget):
         """(B, nh) hyperparameters (+ optional (B,) nuggets) -> device tensors, or None for shared ones."""
         if np.ndim(hyp) != 2:

@@ -207,6 +207,30 @@ int cgp_ll_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
   return run_small(TASK_LL, dim, max_n, a, (cudaStream_t)stream, "cgp_ll_objhyp_dev");
 }
 
+int cgp_fit_objects_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                        const double* x, const double* y, const double* y0, const double* y_err,
+                        const double* start, int n_par, double nugget, double floor, unsigned flags,
+                        double xatol, double fatol, int maxiter, int maxfun,
+                        double* par_out, double* nll_out, int* iterations, int* evaluations, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !y || !start || !par_out || !nll_out || !iterations || !evaluations)))
+    return fail(CGP_ERR_ARG, "cgp_fit_objects_dev: NULL argument");
+  if (dim != 1 && dim != 2) return fail(CGP_ERR_ARG, "dim must be 1 or 2, got %d", dim);
+  const int nh = dim == 1 ? 2 : 4;
+  if (n_par != nh && n_par != nh + 1)
+    return fail(CGP_ERR_ARG, "cgp_fit_objects_dev: n_par must be %d or %d, got %d", nh, nh + 1, n_par);
+  if (n_obj > 2147483647LL) return fail(CGP_ERR_SIZE, "cgp_fit_objects_dev: more than 2^31-1 objects");
+  if (max_n <= 0) return fail(CGP_ERR_ARG, "cgp_fit_objects_dev: max_n is required");
+  if (max_n > CGP_SMALL_MAX_N)
+    return fail(CGP_ERR_SIZE, "cgp_fit_objects_dev: object with %d points exceeds the shared-memory path (max %d)",
+                max_n, CGP_SMALL_MAX_N);
+  if (maxiter <= 0 || maxfun <= 0) return fail(CGP_ERR_ARG, "cgp_fit_objects_dev: maxiter and maxfun must be positive");
+  keep_pool_memory();
+  int e = fit_nelder_mead(n_obj, off, max_n, dim, x, y, y0, y_err, start, n_par, nugget, floor, flags,
+                          xatol, fatol, maxiter, maxfun, par_out, nll_out, iterations, evaluations, (cudaStream_t)stream);
+  if (e) return cuda_fail(e, "cgp_fit_objects_dev");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ predict
 // hyp (shared) or hyp_obj / nugget_obj (per object, device arrays indexed by object id)
 static void set_objhyp(SmallArgs& a, int dim, const double* hyp_obj, const double* nugget_obj, double nugget,

@@ -45,6 +45,8 @@ enum Task { TASK_LL = 0, TASK_PREDICT = 1, TASK_LOO = 2, TASK_MATRICES = 3, TASK
 
 struct SmallArgs {
   int64_t n_obj;
+  const int* n_obj_dev;    // optional: the number of work items is read from device memory (<= n_obj, which
+                           // then only sizes the grid) -- device-side optimiser loops, no host round trip
   const int64_t* off;      // CSR [n_obj+1]
   const int* order;        // optional processing order (object ids), may be null
   const double* x;         // dim doubles per point
@@ -122,6 +124,13 @@ int launch_small64_d2_t4(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d2_t5(int nb, const SmallArgs& a, cudaStream_t stream);
 // doubles per object in the factor workspace for nb blocks of 8 points
 inline int64_t factor_ws_doubles(int nb) { return (int64_t)(nb * (nb + 1) / 2) * 64 + 8 * nb; }
+
+// device-side Nelder-Mead over all objects (cgp_fit.cu); returns cudaError_t as int
+int fit_nelder_mead(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                    const double* x, const double* y, const double* y0, const double* y_err,
+                    const double* x0, int n_par, double nugget, double floor, unsigned flags,
+                    double xatol, double fatol, int maxiter, int maxfun,
+                    double* x_out, double* f_out, int* it_out, int* fc_out, cudaStream_t st);
 
 // FP64 ceiling probes (cgp_small.cu)
 int measure_fp64_peak(int kind, double* tflops);

@@ -181,7 +181,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
   __shared__ int s_bad;
 
   const int split = (TASK == TASK_PREDICT) ? a.split : 1;
-  const int64_t n_work = a.n_obj * split;
+  const int64_t n_work = (a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj) * split;
 
   for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
     const int64_t oi = w / split;

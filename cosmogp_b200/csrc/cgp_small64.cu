@@ -139,7 +139,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   double* vu = v1 + LD;
 
   const int split = (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) ? a.split : 1;
-  const int64_t n_work = a.n_obj * split;
+  const int64_t n_work = (a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj) * split;
   // factor workspace of one object: NT tiles in fragment order followed by alpha (LD doubles)
   constexpr int WS = NT * TILE + LD;
   __shared__ __align__(8) unsigned long long s_mbar;       // TMA completion barrier (TASK_PREDICT_F)
@@ -590,7 +590,7 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   double* px = tiles + NSLOT * TILE;
   double* noise = px + DIM * LD;
   double* vr = noise + LD;
-  const int64_t n_work = a.n_obj;
+  const int64_t n_work = a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj;
 
   constexpr int NR = (LD + 31) / 32;
   struct Next { int64_t b, io; int n; double x[NR], y2[NR], r[NR], ye[NR]; };

@@ -1,4 +1,5 @@
-"""Per-object hyperparameter fits in lock step.
+"""Per-object hyperparameter fits in lock step (host statement; the product path is
+cgp_fit_objects_dev, which keeps the simplices on the device and is tested to give identical results).
 
 The reference fits one object at a time (`gaussian_process(y[i], x[i]).find_hyperparameters()`
 in a Python loop, docs/notebook/1D_kernel_example_with_noise.ipynb cell 13;
@@ -61,8 +62,9 @@ def nelder_mead_lockstep(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfun=N
 
     while len(ids):
         k = len(ids)
-        spread = np.abs(S[:, 1:] - S[:, :1]).reshape(k, -1).max(axis=1)
-        fspread = np.abs(F[:, :1] - F[:, 1:]).max(axis=1)
+        with np.errstate(invalid="ignore"):                  # inf - inf -> NaN -> never "converged", like scipy
+            spread = np.abs(S[:, 1:] - S[:, :1]).reshape(k, -1).max(axis=1)
+            fspread = np.abs(F[:, :1] - F[:, 1:]).max(axis=1)
         keep = (fc < maxfun) & (it < maxiter) & ~((spread <= xatol) & (fspread <= fatol))
         if not keep.all():
             fin = ~keep

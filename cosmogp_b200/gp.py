@@ -216,11 +216,13 @@ class Gaussian_process:
         if self.fit_nugget:
             self.nugget = np.sqrt(hyperparameters[-1] ** 2)
 
-    def find_hyperparameters_per_object(self, hyperparameter_guess=None, nugget=False, svd_method=True):
+    def find_hyperparameters_per_object(self, hyperparameter_guess=None, nugget=False, svd_method=True, optimizer='device'):
         """One maximum-likelihood fit PER OBJECT -- the batched form of the reference's loop
         `for i: gp = gaussian_process(y[i], Time[i], ...); gp.find_hyperparameters(guess)`
         (docs/notebook/1D_kernel_example_with_noise.ipynb cell 13).  scipy's Nelder-Mead is replayed
-        in lock step for all objects (cosmogp_b200.fit); every evaluation is one device launch.
+        for all objects at once; every evaluation is one device launch.  optimizer='device': the
+        simplices live on the device too (cgp_fit_objects_dev, no host round trips); 'host': the numpy
+        statement of the same rules (cosmogp_b200.fit), kept as the cross-check -- both give identical results.
         Sets `hyperparameters_per_object` (N_sn, n_hyp), `nugget_per_object` (N_sn,) and
         `log_likelihood_per_object`; an object whose covariance is not positive definite at a trial
         point gets +inf there (the reference would abort with LinAlgError)."""
@@ -239,7 +241,11 @@ class Gaussian_process:
             f[(info != 0) | ~np.isfinite(f)] = np.inf
             return f
 
-        x, fval, its, calls = nelder_mead_lockstep(fun, x0)
+        assert optimizer in ('device', 'host')
+        if optimizer == 'device' and not self._is_large:
+            x, fval, its, calls = self.batch.fit_objects(x0, nugget=base_nugget, flags=self.flags)
+        else:
+            x, fval, its, calls = nelder_mead_lockstep(fun, x0)
         self.hyperparameters_per_object = np.sqrt(x[:, :nh] ** 2)              # abs, like :249-250
         self.nugget_per_object = np.sqrt(x[:, nh] ** 2) if nugget else np.full(self.N_sn, base_nugget)
         self.log_likelihood_per_object = -fval

@@ -86,6 +86,20 @@ int cgp_ll_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
                       const double* hyp_obj, const double* nugget_obj, double nugget, double floor, unsigned flags,
                       const int* order, int64_t n_active, double* ll_obj, int* info, void* stream);
 
+/* The whole per-object fit on the device: scipy.optimize.fmin's Nelder-Mead (what
+ * Gaussian_process.py:246-247 calls) as one state machine per object, the objective of all pending
+ * trial points evaluated by one batched likelihood launch per step; the host only enqueues launches.
+ * start, par_out: (n_obj, n_par) device arrays, n_par = nh (nugget fixed to `nugget`) or nh+1 (the last
+ * parameter is the object's nugget, Gaussian_process.py:241-245).  nll_out = -log-likelihood at par_out
+ * (+inf where the covariance never was positive definite), iterations / evaluations as scipy reports
+ * them.  xatol, fatol, maxiter, maxfun as in scipy (fmin defaults: 1e-4, 1e-4, 200*n_par, 200*n_par).
+ * Synchronises the stream before returning. */
+int cgp_fit_objects_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                        const double* x, const double* y, const double* y0, const double* y_err,
+                        const double* start, int n_par, double nugget, double floor, unsigned flags,
+                        double xatol, double fatol, int maxiter, int maxfun,
+                        double* par_out, double* nll_out, int* iterations, int* evaluations, void* stream);
+
 /* prediction and pulls with per-object hyperparameters (hyp_obj / nugget_obj indexed by object id):
  * the rest of the reference's per-object loop (fit, predict, build_pull with each object's own fit). */
 int cgp_predict_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,

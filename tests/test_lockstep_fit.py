@@ -82,3 +82,43 @@ def test_per_object_predict_and_pulls():
             assert_close(gp.Prediction[i], mo, 1e-9, 1e-12); assert_close(gp.prediction_variance[i], vo, 1e-9, 1e-13)
             po = O.loo_closed_form(y[i], x[i], hyp[i], nug[i], ye[i])
             assert_close(bp._pull[i], po[2], 1e-9, 1e-11)
+
+
+@pytest.mark.gpu
+def test_device_optimiser_equals_host_lockstep():
+    """cgp_fit_objects_dev (simplices on the device) takes the same decisions as the numpy
+    lock-step replay of scipy's Nelder-Mead: identical parameters, objective, iteration and
+    evaluation counts, object by object -- 1D, 1D with a fitted nugget, ragged sizes across the
+    one-warp and generic kernels, and 2D; including objects that never become positive definite."""
+    import cosmogp_b200 as cg
+    rng = np.random.default_rng(33)
+
+    def both(gp, guess, nugget):
+        gp.find_hyperparameters_per_object(hyperparameter_guess=guess, nugget=nugget, optimizer='device')
+        dev = (gp.hyperparameters_per_object.copy(), gp.nugget_per_object.copy(), gp.log_likelihood_per_object.copy(),
+               gp.fit_iterations.copy(), gp.fit_evaluations.copy())
+        gp.find_hyperparameters_per_object(hyperparameter_guess=guess, nugget=nugget, optimizer='host')
+        host = (gp.hyperparameters_per_object, gp.nugget_per_object, gp.log_likelihood_per_object,
+                gp.fit_iterations, gp.fit_evaluations)
+        for d, h in zip(dev, host):
+            np.testing.assert_array_equal(d, h)
+        return dev
+
+    g = golden("notebook_with_noise")
+    both(cg.gaussian_process_nobject(g["y"], g["x"], y_err=g["y_err"]), [0.5, 2], False)
+    both(cg.gaussian_process_nobject(g["y"][:40], g["x"][:40], y_err=g["y_err"][:40]), [0.5, 2], True)
+
+    sizes = rng.integers(3, 120, 300)                       # ragged, crossing N = 64
+    x = [np.sort(rng.uniform(0, 30, n)) for n in sizes]
+    y = [np.sin(t / 3.0) + 0.2 * rng.standard_normal(len(t)) for t in x]
+    ye = [np.full(len(t), 0.2) for t in x]
+    y[7] = np.full(len(y[7]), np.nan)                       # never positive definite: +inf everywhere
+    d = both(cg.gaussian_process_nobject(y, x, y_err=ye), [1.0, 3.0], False)
+    assert np.isinf(d[2][7]) and d[4][7] >= 400             # never finite: runs into maxfun like scipy would
+
+    b, n = 64, 25                                           # 2D
+    xy = [rng.uniform(0, 10, (n, 2)) for _ in range(b)]
+    z = [np.sin(p[:, 0]) * np.cos(p[:, 1]) + 0.1 * rng.standard_normal(n) for p in xy]
+    ze = [np.full(n, 0.1) for _ in range(b)]
+    both(cg.gaussian_process_nobject(z, xy, kernel='RBF2D', y_err=ze), [1.0, 2.0, 2.0, 0.1], False)
+    both(cg.gaussian_process_nobject(z[:16], xy[:16], kernel='RBF2D', y_err=ze[:16]), [1.0, 2.0, 2.0, 0.1], True)
