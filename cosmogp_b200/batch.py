@@ -265,25 +265,36 @@ class DeviceBatch:
         _lib.check(rc, "cgp_factor_batched_dev")
         return {"ws": ws, "hyp": h, "nugget": float(nugget), "flags": int(flags)}
 
-    def predict_factored_dev(self, fac, grid, goff=None, new_y0=None, want_var=True):
-        """Prediction from a factor_dev() workspace; same outputs as predict_dev."""
+    def predict_factored_dev(self, fac, grid, goff=None, new_y0=None, want_var=True, template_mean=False):
+        """Prediction from a factor_dev() workspace; same outputs as predict_dev.  template_mean: new_y0 is
+        the packed shared mean [template on the grid (M) | per-object offsets (B)] (CGP_MEAN_TEMPLATE)."""
         m = 0 if goff is not None else int(grid.shape[0])
         nout = int(goff[-1].item()) if goff is not None else self.n_obj * m
         mean = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device)
         var = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device) if want_var else None
         with torch.cuda.device(self.device):
             rc = _lib.lib().cgp_predict_factored_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
-                                                     _lib.hptr(fac["hyp"]), fac["nugget"], fac["flags"], self._p(fac["ws"]),
+                                                     _lib.hptr(fac["hyp"]), fac["nugget"],
+                                                     fac["flags"] | (_lib.CGP_MEAN_TEMPLATE if template_mean else 0), self._p(fac["ws"]),
                                                      self._p(self._info), self._p(grid), self._p(goff), m,
                                                      self._p(new_y0), self._p(mean), self._p(var), self._stream())
         _lib.check(rc, "cgp_predict_factored_dev")
         return mean[:nout], (var[:nout] if want_var else None), self._info[:self.n_obj]
 
-    def predict(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0):
+    def predict(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0, mean_template=None):
         """grid: host array, shared (M,[2]) or per-object flat with goff (int64 B+1).
+        new_y0: the mean function on the grid, one row per object; or mean_template=(template (M,),
+        offsets (B,)) for a shared template plus one offset per object (shared grid only): only M + B
+        doubles are uploaded instead of B x M.
         -> mean, var (host; shape (B,M) for a shared grid, flat otherwise), info."""
         g = self._up(np.asarray(grid, dtype=np.float64))
         go = self._up(np.asarray(goff, dtype=np.int64)) if goff is not None else None
+        if mean_template is not None:
+            assert goff is None and new_y0 is None
+            tmpl, diff = mean_template
+            packed = np.concatenate([np.asarray(tmpl, dtype=np.float64).ravel(), np.asarray(diff, dtype=np.float64).ravel()])
+            assert packed.size == int(g.shape[0]) + self.n_obj, "template must cover the grid, offsets the objects"
+            new_y0, flags = packed, int(flags) | _lib.CGP_MEAN_TEMPLATE
         ny0 = self._up(np.asarray(new_y0, dtype=np.float64)) if new_y0 is not None else None
         mean, var, info = self.predict_dev(hyp, nugget, g, go, ny0, want_var, floor, flags)
         mean_h = self._down(mean)
@@ -353,9 +364,12 @@ class StreamedEvaluator:
     streams while chunk k-1 computes and chunk k-2 downloads (PCIe is full duplex), so the
     end-to-end time approaches max(copy, compute) instead of their sum.  Inputs and outputs
     are pinned host arrays owned by this object; equal-length objects only (x, y, y0, y_err of
-    shape (B, N)), shared prediction grid."""
+    shape (B, N)), shared prediction grid.  The mean function on the grid is either "new_y0" (B, M)
+    or, with shared_mean=True, "template" (M,) + "diff" (B,) -- the reference's own inputs
+    (Mean_Y interpolated on the grid, plus diff[sn]; mean.py:92-101) -- which saves 8 M bytes of
+    upload per object."""
 
-    def __init__(self, n_obj, n_pts, m_grid, dim=1, n_chunks=8, n_streams=3, device=None):
+    def __init__(self, n_obj, n_pts, m_grid, dim=1, n_chunks=8, n_streams=3, device=None, shared_mean=False):
         _lib.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.B, self.N, self.M, self.dim = int(n_obj), int(n_pts), int(m_grid), int(dim)
@@ -364,15 +378,28 @@ class StreamedEvaluator:
         self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
         xs = (self.B, self.N, 2) if dim == 2 else (self.B, self.N)
         pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        self.shared_mean = bool(shared_mean)
         self.h = {"x": pin(*xs), "y": pin(self.B, self.N), "y0": pin(self.B, self.N), "y_err": pin(self.B, self.N),
-                  "new_y0": pin(self.B, self.M), "ll": pin(self.B), "mean": pin(self.B, self.M), "var": pin(self.B, self.M)}
+                  "ll": pin(self.B), "mean": pin(self.B, self.M), "var": pin(self.B, self.M)}
+        if self.shared_mean:
+            self.h["template"], self.h["diff"] = pin(self.M), pin(self.B)
+        else:
+            self.h["new_y0"] = pin(self.B, self.M)
         self.h_info = torch.empty(self.B, dtype=torch.int32, pin_memory=True)
         dev = lambda *shape: torch.empty(shape, dtype=torch.float64, device=self.device)
         dxs = (cmax, self.N, 2) if dim == 2 else (cmax, self.N)
         self.d = [{"x": dev(*dxs), "y": dev(cmax, self.N), "y0": dev(cmax, self.N), "y_err": dev(cmax, self.N),
-                   "new_y0": dev(cmax, self.M), "ll": dev(cmax), "mean": dev(cmax, self.M), "var": dev(cmax, self.M),
+                   "new_y0": dev(self.M + cmax) if self.shared_mean else dev(cmax, self.M),   # packed [template | offsets]
+                   "ll": dev(cmax), "mean": dev(cmax, self.M), "var": dev(cmax, self.M),
                    "info": torch.empty(cmax, dtype=torch.int32, device=self.device),
                    "off": (torch.arange(cmax + 1, dtype=torch.int64) * self.N).to(self.device)} for _ in range(n_streams)]
+        # objects of <= 64 points: factor + grid kernels called directly on a per-stream factor workspace
+        # (what cgp_predict_batched_dev does internally, minus its stream-ordered allocation per call)
+        self.two_kernel = self.N <= 64 and cmax >= 2048
+        if self.two_kernel:
+            stride = int(_lib.lib().cgp_factor_ws_doubles(self.N))
+            for d in self.d:
+                d["ws"] = dev(cmax * stride)
         self.h2d_bytes = self.d2h_bytes = 0
 
     def host(self, name):
@@ -394,16 +421,32 @@ class StreamedEvaluator:
                 continue
             st, d = self.streams[k % len(self.streams)], self.d[k % len(self.streams)]
             with torch.cuda.stream(st):
-                for name in ("x", "y", "y0", "y_err", "new_y0"):
+                for name in ("x", "y", "y0", "y_err") + (() if self.shared_mean else ("new_y0",)):
                     d[name][:nb].copy_(self.h[name][a:b], non_blocking=True)
                     self.h2d_bytes += self.h[name][a:b].numel() * 8
+                if self.shared_mean:
+                    if k < len(self.streams):                 # first use of this buffer set in this run
+                        d["new_y0"][:self.M].copy_(self.h["template"], non_blocking=True)
+                        self.h2d_bytes += self.M * 8
+                    d["new_y0"][self.M:self.M + nb].copy_(self.h["diff"][a:b], non_blocking=True)
+                    self.h2d_bytes += nb * 8
                 _lib.check(L.cgp_ll_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
                                                 p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), int(flags),
                                                 p(d["ll"]), p(d["info"]), st.cuda_stream), "cgp_ll_batched_dev")
-                _lib.check(L.cgp_predict_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
-                                                     p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), int(flags),
-                                                     p(g), None, self.M, p(d["new_y0"]), p(d["mean"]), p(d["var"]),
-                                                     p(d["info"]), st.cuda_stream), "cgp_predict_batched_dev")
+                pflags = int(flags) | (_lib.CGP_MEAN_TEMPLATE if self.shared_mean else 0)
+                if self.two_kernel:
+                    _lib.check(L.cgp_factor_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
+                                                        p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), int(flags),
+                                                        p(d["ws"]), p(d["info"]), st.cuda_stream), "cgp_factor_batched_dev")
+                    _lib.check(L.cgp_predict_factored_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), _lib.hptr(h),
+                                                          float(nugget), pflags, p(d["ws"]), p(d["info"]), p(g), None, self.M,
+                                                          p(d["new_y0"]), p(d["mean"]), p(d["var"]), st.cuda_stream),
+                               "cgp_predict_factored_dev")
+                else:
+                    _lib.check(L.cgp_predict_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
+                                                         p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), pflags,
+                                                         p(g), None, self.M, p(d["new_y0"]), p(d["mean"]), p(d["var"]),
+                                                         p(d["info"]), st.cuda_stream), "cgp_predict_batched_dev")
                 self.h["ll"][a:b].copy_(d["ll"][:nb], non_blocking=True)
                 self.h["mean"][a:b].copy_(d["mean"][:nb], non_blocking=True)
                 self.h["var"][a:b].copy_(d["var"][:nb], non_blocking=True)

@@ -258,6 +258,11 @@ static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
   if (n_obj && max_n <= 0 && (rc = max_n_from_device(n_obj, off, st, &max_n))) return rc;
   a.n_obj = n_obj; a.off = off; a.x = x; a.y = y; a.y0 = y0; a.yerr = y_err; a.info = info;
   a.xnew = xnew; a.goff = goff; a.m_shared = m_shared; a.new_y0 = new_y0; a.mean = mean; a.var = var;
+  const bool tmpl = (flags & CGP_MEAN_TEMPLATE) && new_y0;
+  if (tmpl) {
+    if (goff) return fail(CGP_ERR_ARG, "CGP_MEAN_TEMPLATE needs a shared grid (goff == NULL)");
+    a.new_y0_diff = new_y0 + m_shared;
+  }
   // few objects with long grids: several CTAs per object, each refactorising (cheap) and
   // taking every split-th block of 8 grid points
   int split = 1;
@@ -289,7 +294,11 @@ static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
       f.n_obj = n_obj - c0 < chunk ? n_obj - c0 : chunk;
       f.off = off + c0; f.info = info + c0;
       if (goff) f.goff = goff + c0;
-      else { f.mean = mean + c0 * m_shared; f.var = var + c0 * m_shared; if (new_y0) f.new_y0 = new_y0 + c0 * m_shared; }
+      else {
+        f.mean = mean + c0 * m_shared; f.var = var + c0 * m_shared;
+        if (tmpl) f.new_y0_diff = a.new_y0_diff + c0;
+        else if (new_y0) f.new_y0 = new_y0 + c0 * m_shared;
+      }
       f.fws = ws; f.fws_stride = stride;
       if (hyp_obj) { f.hyp_obj = hyp_obj + c0 * f.n_hyp; if (nugget_obj) f.nugget_obj = nugget_obj + c0; }
       rc2 = run_small(TASK_FACTOR, dim, max_n, f, st, "cgp_predict_batched_dev (factor)");
@@ -341,7 +350,7 @@ int cgp_predict_batched_host(int64_t n_obj, const int64_t* off, int dim,
   const double* d_e = hc.up(b_e, y_err, np);
   const double* d_g = hc.up(b_g, xnew, ng * dim);
   const int64_t* d_goff = hc.up(b_goff, goff, (size_t)n_obj + 1);
-  const double* d_ny0 = hc.up(b_ny0, new_y0, nout);
+  const double* d_ny0 = hc.up(b_ny0, new_y0, (flags & CGP_MEAN_TEMPLATE) ? (size_t)m_shared + (size_t)n_obj : nout);
   double* d_mean = hc.out(b_mean, mean, nout);
   double* d_var = hc.out(b_var, var, nout);
   int* d_info = hc.out(b_info, info, (size_t)n_obj);
@@ -389,6 +398,10 @@ int cgp_predict_factored_dev(int64_t n_obj, const int64_t* off, int max_n, int d
   a.n_obj = n_obj; a.off = off; a.x = x; a.info = const_cast<int*>(info);
   a.fws = const_cast<double*>(ws); a.fws_stride = cgp_factor_ws_doubles(max_n);
   a.xnew = xnew; a.goff = goff; a.m_shared = m_shared; a.new_y0 = new_y0; a.mean = mean; a.var = var;
+  if ((flags & CGP_MEAN_TEMPLATE) && new_y0) {
+    if (goff) return fail(CGP_ERR_ARG, "CGP_MEAN_TEMPLATE needs a shared grid (goff == NULL)");
+    a.new_y0_diff = new_y0 + m_shared;
+  }
   int split = 1;
   if (!goff && n_obj < 296) {
     const int64_t rbs = (m_shared + 7) / 8;

@@ -18,6 +18,7 @@ struct Cov {
 };
 
 #define CGP_FLAG_AMP_ON_AUTOCOV 1u
+#define CGP_FLAG_MEAN_TEMPLATE 2u
 
 // hyp -> Cov (cosmogp/kernel.py:71-75 for 1D, :127-151 for 2D); shared by the host API and by the
 // kernels when every object carries its own hyperparameters.  A singular / NaN metric propagates.
@@ -66,6 +67,7 @@ struct SmallArgs {
   const int64_t* goff;     // null -> shared grid of m_shared points
   int64_t m_shared;
   const double* new_y0;    // may be null
+  const double* new_y0_diff; // non-null: new_y0 is ONE shared row (m_shared values) and object b adds new_y0_diff[b]
   double* mean;
   double* var;             // may be null
   int split;               // CTAs per object (each takes every split-th block of 8 grid points)

@@ -511,7 +511,8 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
         for (int J = 0; J < NB_MAX; ++J) { vv = fma(acc0[J], acc0[J], vv); vv2 = fma(acc1[J], acc1[J], vv2); }
         pm = red_t(pm + pm2); vv = red_t(vv + vv2);
         if (live && L.t == 0) {
-          double mean = fma(cov.amp_cross, pm, a.new_y0 ? a.new_y0[out0 + mi] : 0.0);
+          const double m0 = !a.new_y0 ? 0.0 : (a.new_y0_diff ? a.new_y0[mi] + a.new_y0_diff[b] : a.new_y0[out0 + mi]);
+          double mean = fma(cov.amp_cross, pm, m0);
           double var = fma(-cov.amp_cross * cov.amp_cross, vv, amp_star);
           if (bad) { mean = nan(""); var = mean; }
           a.mean[out0 + mi] = mean;

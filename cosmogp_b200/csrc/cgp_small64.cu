@@ -488,7 +488,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
             if (DIM == 1) pgx[u] = a.xnew[g0 + m];
             else { pgx[u] = a.xnew[2 * (g0 + m)]; pgy[u] = a.xnew[2 * (g0 + m) + 1]; }
           }
-          pny0[u] = (lv && a.new_y0) ? a.new_y0[out0 + m] : 0.0;
+          pny0[u] = (lv && a.new_y0) ? (a.new_y0_diff ? a.new_y0[m] + a.new_y0_diff[b] : a.new_y0[out0 + m]) : 0.0;
         }
       };
       grid_fetch((int64_t)part * 2);

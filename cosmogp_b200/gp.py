@@ -50,6 +50,24 @@ class _LazyMatrices(object):
         return (self[i] for i in range(self._n))
 
 
+class _LazyMeanOnGrid:
+    """`warning_pf` of a shared-grid prediction: template + diff[sn], row sn built on access."""
+
+    def __init__(self, template, diff):
+        self.template, self.diff = np.asarray(template), np.asarray(diff)
+        self.shape = (len(self.diff), len(self.template))
+
+    def __len__(self):
+        return len(self.diff)
+
+    def __getitem__(self, i):
+        return np.asarray(self)[i] if not isinstance(i, (int, np.integer)) else self.template + self.diff[i]
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.template[None, :] + self.diff[:, None]
+        return out if dtype is None else out.astype(dtype)
+
+
 class Gaussian_process:
     "Gaussian process regressor (device-backed)."
 
@@ -324,17 +342,15 @@ class Gaussian_process:
             self.new_binning = new_binning
             grid = np.ascontiguousarray(new_binning, dtype=np.float64)
             m = len(grid)
-            new_y0 = None
+            new_y0 = mean_template = None
             if has_mean:                                                    # :310-312 via mean.py:92-101
+                # mean on the grid = template(grid) + diff[sn]; without a template return_mean hands back
+                # y0 (= diff) for any new_x.  Only the M template values and the N_sn offsets are uploaded.
                 tmpl = _mean.template_on_grid(grid, self._dim, self.Mean_Y, self.Time_mean)
-                if tmpl is not None:
-                    new_y0 = tmpl[None, :] + self._diff_used[:, None]
-                else:
-                    # no template: return_mean hands back y0 (per-epoch constant = diff) for any new_x;
-                    # it only broadcasts in the reference when it is a scalar per object
-                    new_y0 = np.repeat(self._diff_used[:, None], m, axis=1)
+                mean_template = (np.zeros(m) if tmpl is None else tmpl, self._diff_used)
+                new_y0 = _LazyMeanOnGrid(*mean_template)
             mean, var, info = self.batch.predict(hyp_b if per_object else hyp, nug_b if per_object else nug, grid,
-                                                 new_y0=new_y0, want_var=want_var, flags=self.flags)
+                                                 mean_template=mean_template, want_var=want_var, flags=self.flags)
             self._raise_if_bad(info)
             self.Prediction = list(mean)
             self.prediction_variance = list(var) if want_var else None

@@ -31,6 +31,12 @@
  *           [sigma, l_x, l_y, l_xy] (dim 2, cosmogp/kernel.py:80-155).
  *   - flags: CGP_AMP_ON_AUTOCOV applies sigma^2 to the 2D auto-covariance; the
  *     default (0) reproduces HEAD, which omits it (kernel.py:146-148).
+ *     CGP_MEAN_TEMPLATE (prediction entry points, shared grid only): new_y0 is
+ *     not one row per object but the SHARED mean template on the grid (m_shared
+ *     values) followed by one offset per object (n_obj values, the reference's
+ *     `diff`): mean function of object b at grid point j = new_y0[j] +
+ *     new_y0[m_shared + b] -- what mean.py:92-101 evaluates per object, without
+ *     materialising (or uploading) n_obj x m_shared doubles.
  *   - all arithmetic is IEEE float64.
  */
 #ifndef COSMOGP_B200_H
@@ -43,6 +49,7 @@ extern "C" {
 #endif
 
 #define CGP_AMP_ON_AUTOCOV 1u      /* opt-in fix of the 2D sigma^2 omission */
+#define CGP_MEAN_TEMPLATE  2u      /* new_y0 = [template on the shared grid | per-object offsets] */
 
 #define CGP_SMALL_MAX_N 224        /* largest object the shared-memory path takes */
 

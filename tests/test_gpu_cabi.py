@@ -366,6 +366,46 @@ def test_factor_once_predict_many(L):
     assert_close(mf.cpu().numpy().reshape(5, 500), ms, 1e-13, 1e-13); assert_close(vf.cpu().numpy().reshape(5, 500), vs, 1e-13, 1e-14)
 
 
+def test_shared_mean_template_flag(L):
+    """CGP_MEAN_TEMPLATE: new_y0 = [template on the shared grid | one offset per object] gives exactly the
+    results of the materialised (n_obj x M) mean -- fused kernel, generic kernel (N > 64), the two-kernel
+    route of large batches, the factored entry point, and 2D; per-object grids are refused."""
+    import torch
+    from cosmogp_b200.batch import DeviceBatch
+    rng = np.random.default_rng(5)
+    hyp, nug = [0.6, 2.5], 0.04
+    for b, n, m in ((7, 30, 45), (5, 100, 33), (2500, 40, 50)):
+        x = np.sort(rng.uniform(-10, 40, (b, n)), axis=1); y = rng.standard_normal((b, n)); ye = rng.uniform(0.1, 0.3, (b, n))
+        grid = np.linspace(-12, 42, m); tmpl = np.sin(grid / 7.0); diff = rng.standard_normal(b)
+        full = tmpl[None, :] + diff[:, None]
+        m1, v1, _ = run_predict(L, list(x), list(y), None, list(ye), hyp, nug, grid, new_y0=full)
+        m2, v2, _ = run_predict(L, list(x), list(y), None, list(ye), hyp, nug, grid, new_y0=np.concatenate([tmpl, diff]),
+                                flags=L.CGP_MEAN_TEMPLATE)
+        assert np.array_equal(m1, m2) and np.array_equal(v1, v2)
+        mo, _ = O.predict(y[b // 2], x[b // 2], hyp, nug, grid, ye[b // 2], np.zeros(n), full[b // 2], full_cov=False)
+        assert_close(m2[b // 2], mo, RTOL, 1e-12)
+        if n <= 64:
+            batch = DeviceBatch(x.ravel(), y.ravel(), np.arange(b + 1, dtype=np.int64) * n, y_err=ye.ravel())
+            fac = batch.factor_dev(hyp, nug)
+            packed = torch.from_numpy(np.concatenate([tmpl, diff])).cuda()
+            m3, v3, _ = batch.predict_factored_dev(fac, torch.from_numpy(grid).cuda(), None, packed, True, template_mean=True)
+            m4, v4, _ = batch.predict_factored_dev(fac, torch.from_numpy(grid).cuda(), None, torch.from_numpy(full).cuda(), True)
+            assert torch.equal(m3, m4) and torch.equal(v3, v4)
+            m5, _, _ = batch.predict(hyp, nug, grid, mean_template=(tmpl, diff))
+            assert np.array_equal(m5, m1)
+    b, n, m = 9, 20, 30                                   # 2D
+    xy = rng.uniform(0, 10, (b, n, 2)); z = rng.standard_normal((b, n)); ze = np.full((b, n), 0.2)
+    grid = rng.uniform(0, 10, (m, 2)); tmpl = rng.standard_normal(m); diff = rng.standard_normal(b)
+    h2 = [1.0, 2.0, 1.5, 0.3]
+    m1, v1, _ = run_predict(L, list(xy), list(z), None, list(ze), h2, 0.05, grid, new_y0=tmpl[None, :] + diff[:, None], dim=2)
+    m2, v2, _ = run_predict(L, list(xy), list(z), None, list(ze), h2, 0.05, grid, new_y0=np.concatenate([tmpl, diff]), dim=2,
+                            flags=L.CGP_MEAN_TEMPLATE)
+    assert np.array_equal(m1, m2) and np.array_equal(v1, v2)
+    x = [np.arange(5.0)]; goff = np.array([0, 5], dtype=np.int64)
+    with pytest.raises(RuntimeError):
+        run_predict(L, x, [np.ones(5)], None, None, hyp, nug, np.arange(5.0), new_y0=np.zeros(6), goff=goff, flags=L.CGP_MEAN_TEMPLATE)
+
+
 def test_degenerate_inputs(L):
     """Empty batches, empty grids, NaN / singular hyperparameters: defined outputs, no crash."""
     rng = np.random.default_rng(3)

@@ -159,6 +159,15 @@ def test_streamed_evaluator_matches_resident_batch(cg):
     assert not info.any() and tot == t2
     assert np.array_equal(ll, ll2) and np.array_equal(mean, m2) and np.array_equal(var, v2)
     assert ev.h2d_bytes == b * (4 * n + m) * 8 and ev.d2h_bytes == b * (8 + 16 * m + 4)
+    # shared mean (template + offset per object): same results from M + B mean values instead of B x M
+    tmpl, diff = np.cos(grid / 5.0), rng.standard_normal(b)
+    ev2 = StreamedEvaluator(b, n, m, n_chunks=7, shared_mean=True)
+    for k, v in (("x", x), ("y", y), ("y0", y0), ("y_err", ye), ("template", tmpl), ("diff", diff)):
+        ev2.host(k)[...] = v
+    tot3, ll3, mean3, var3, info3 = ev2.run([0.5, 2.0], 0.03, grid)
+    m4, v4, _ = batch.predict([0.5, 2.0], 0.03, grid, new_y0=tmpl[None, :] + diff[:, None])
+    assert tot3 == t2 and np.array_equal(mean3, m4) and np.array_equal(var3, v4)
+    assert ev2.h2d_bytes == (b * (4 * n + 1) + 3 * m) * 8
 
 
 def test_large_objects_through_the_facade(cg):
