@@ -15,6 +15,7 @@
 //       generated first, then 4 NB(NB+1)/2 DMMAs on 4 NB independent accumulators
 // Objects with fewer than NB blocks are padded with identity rows (exact, just wasteful);
 // per-object n masks the covariance entries.  Reference: see cgp_small.cu header.
+#include <atomic>
 #include "cgp_internal.h"
 #include "cgp_math.cuh"
 
@@ -100,14 +101,14 @@ __device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
 
 // Ring of work counters (one per launch in flight), zeroed in stream order before each launch.
 static unsigned long long* next_ticket(cudaStream_t stream) {
-  constexpr unsigned RING = 256;
+  constexpr unsigned RING = 4096;                         // launches that may be in flight on different streams
   constexpr int MAX_DEV = 16;
   static unsigned long long* ring[MAX_DEV] = {nullptr};   // one ring per device of this process
-  static unsigned idx[MAX_DEV] = {0};
+  static std::atomic<unsigned> idx[MAX_DEV];             // host threads may launch concurrently
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
   if (!ring[dev] && cudaMalloc((void**)&ring[dev], RING * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
-  unsigned long long* t = ring[dev] + (idx[dev]++ % RING);
+  unsigned long long* t = ring[dev] + (idx[dev].fetch_add(1) % RING);
   if (cudaMemsetAsync(t, 0, sizeof(unsigned long long), stream) != cudaSuccess) return nullptr;
   return t;
 }
