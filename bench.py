@@ -258,10 +258,11 @@ def main():
         total_ms = float(t.item())
 
     # ---- end to end through the numpy-in/numpy-out layer: every step uploads the step's inputs from
-    # pinned host memory, runs LL + predict and downloads ll/mean/var; chunks of objects are
-    # pipelined over 10 streams so PCIe (both directions) overlaps the kernels
+    # pinned host memory, runs LL + predict and downloads ll/mean/var; chunks of objects (ramping up from
+    # 2048 to a quarter of the batch and down again) are pipelined: one upload stream, one download stream,
+    # kernels of consecutive chunks on 3 compute streams -- one native call per step (cgp_streamer_run)
     from cosmogp_b200.batch import StreamedEvaluator
-    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "40")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "10")), shared_mean=True)
+    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "4")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "3")), shared_mean=True)
     for name, arr in (("x", x), ("y", y), ("y0", y0.reshape(B, N_EPOCH)), ("y_err", ye), ("template", tmpl), ("diff", d)):
         ev_e2e.host(name)[...] = arr
 

@@ -358,49 +358,48 @@ class DeviceBatch:
 
 
 class StreamedEvaluator:
-    """LL + prediction of a host-resident batch with copies and kernels overlapped.
+    """LL + prediction of a host-resident batch with copies and kernels overlapped (cgp_streamer_*).
 
     The batch is cut into chunks of objects; chunk k is uploaded on one of `n_streams` CUDA
     streams while chunk k-1 computes and chunk k-2 downloads (PCIe is full duplex), so the
-    end-to-end time approaches max(copy, compute) instead of their sum.  Inputs and outputs
-    are pinned host arrays owned by this object; equal-length objects only (x, y, y0, y_err of
-    shape (B, N)), shared prediction grid.  The mean function on the grid is either "new_y0" (B, M)
-    or, with shared_mean=True, "template" (M,) + "diff" (B,) -- the reference's own inputs
-    (Mean_Y interpolated on the grid, plus diff[sn]; mean.py:92-101) -- which saves 8 M bytes of
-    upload per object."""
+    end-to-end time approaches max(copy, compute) instead of their sum.  The chunk loop (about a
+    dozen copies and launches per chunk) runs inside the library: one native call per run().
+    Inputs and outputs are pinned host arrays owned by this object; equal-length objects only
+    (x, y, y0, y_err of shape (B, N)), shared prediction grid.  The mean function on the grid is
+    either "new_y0" (B, M) or, with shared_mean=True, "template" (M,) + "diff" (B,) -- the
+    reference's own inputs (Mean_Y interpolated on the grid, plus diff[sn]; mean.py:92-101) -- which
+    saves 8 M bytes of upload per object."""
 
     def __init__(self, n_obj, n_pts, m_grid, dim=1, n_chunks=8, n_streams=3, device=None, shared_mean=False):
         _lib.require_device()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.B, self.N, self.M, self.dim = int(n_obj), int(n_pts), int(m_grid), int(dim)
-        self.bounds = np.linspace(0, self.B, min(n_chunks, max(self.B, 1)) + 1).astype(np.int64)
-        cmax = int(np.diff(self.bounds).max()) if self.B else 1
-        self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
+        self.chunk = max(1, -(-self.B // max(1, min(int(n_chunks), max(self.B, 1)))))
         xs = (self.B, self.N, 2) if dim == 2 else (self.B, self.N)
         pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
         self.shared_mean = bool(shared_mean)
         self.h = {"x": pin(*xs), "y": pin(self.B, self.N), "y0": pin(self.B, self.N), "y_err": pin(self.B, self.N),
                   "ll": pin(self.B), "mean": pin(self.B, self.M), "var": pin(self.B, self.M)}
         if self.shared_mean:
-            self.h["template"], self.h["diff"] = pin(self.M), pin(self.B)
+            self._packed_mean = pin(self.M + self.B)                # [template | offsets], what CGP_MEAN_TEMPLATE reads
+            self.h["template"], self.h["diff"] = self._packed_mean[:self.M], self._packed_mean[self.M:]
         else:
             self.h["new_y0"] = pin(self.B, self.M)
         self.h_info = torch.empty(self.B, dtype=torch.int32, pin_memory=True)
-        dev = lambda *shape: torch.empty(shape, dtype=torch.float64, device=self.device)
-        dxs = (cmax, self.N, 2) if dim == 2 else (cmax, self.N)
-        self.d = [{"x": dev(*dxs), "y": dev(cmax, self.N), "y0": dev(cmax, self.N), "y_err": dev(cmax, self.N),
-                   "new_y0": dev(self.M + cmax) if self.shared_mean else dev(cmax, self.M),   # packed [template | offsets]
-                   "ll": dev(cmax), "mean": dev(cmax, self.M), "var": dev(cmax, self.M),
-                   "info": torch.empty(cmax, dtype=torch.int32, device=self.device),
-                   "off": (torch.arange(cmax + 1, dtype=torch.int64) * self.N).to(self.device)} for _ in range(n_streams)]
-        # objects of <= 64 points: factor + grid kernels called directly on a per-stream factor workspace
-        # (what cgp_predict_batched_dev does internally, minus its stream-ordered allocation per call)
-        self.two_kernel = self.N <= 64 and cmax >= 2048
-        if self.two_kernel:
-            stride = int(_lib.lib().cgp_factor_ws_doubles(self.N))
-            for d in self.d:
-                d["ws"] = dev(cmax * stride)
+        self._handle = _lib.C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cgp_streamer_create(self.chunk, self.N, self.M, self.dim, int(n_streams),
+                                                      _lib.C.byref(self._handle)), "cgp_streamer_create")
         self.h2d_bytes = self.d2h_bytes = 0
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().cgp_streamer_destroy(h)
+            except Exception:
+                pass
+            h.value = None
 
     def host(self, name):
         """numpy view of a pinned staging array: fill inputs / read outputs in place."""
@@ -408,52 +407,18 @@ class StreamedEvaluator:
 
     def run(self, hyp, nugget, grid, floor=0.0, flags=0):
         """-> (ll_sum, ll (B,), mean (B,M), var (B,M), info (B,)) as numpy views of the pinned outputs."""
-        L = _lib.lib()
+        C = _lib.C
         h = np.ascontiguousarray(np.asarray(hyp, dtype=np.float64).ravel())
-        g = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float64)).to(self.device)
-        torch.cuda.current_stream(self.device).synchronize()
-        self.h2d_bytes = self.d2h_bytes = 0
+        g = np.ascontiguousarray(grid, dtype=np.float64)
+        assert g.shape[0] == self.M, "grid must have the %d points the evaluator was built for" % self.M
         p = lambda t: t.data_ptr()
-        for k in range(len(self.bounds) - 1):
-            a, b = int(self.bounds[k]), int(self.bounds[k + 1])
-            nb = b - a
-            if nb == 0:
-                continue
-            st, d = self.streams[k % len(self.streams)], self.d[k % len(self.streams)]
-            with torch.cuda.stream(st):
-                for name in ("x", "y", "y0", "y_err") + (() if self.shared_mean else ("new_y0",)):
-                    d[name][:nb].copy_(self.h[name][a:b], non_blocking=True)
-                    self.h2d_bytes += self.h[name][a:b].numel() * 8
-                if self.shared_mean:
-                    if k < len(self.streams):                 # first use of this buffer set in this run
-                        d["new_y0"][:self.M].copy_(self.h["template"], non_blocking=True)
-                        self.h2d_bytes += self.M * 8
-                    d["new_y0"][self.M:self.M + nb].copy_(self.h["diff"][a:b], non_blocking=True)
-                    self.h2d_bytes += nb * 8
-                _lib.check(L.cgp_ll_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
-                                                p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), int(flags),
-                                                p(d["ll"]), p(d["info"]), st.cuda_stream), "cgp_ll_batched_dev")
-                pflags = int(flags) | (_lib.CGP_MEAN_TEMPLATE if self.shared_mean else 0)
-                if self.two_kernel:
-                    _lib.check(L.cgp_factor_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
-                                                        p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), int(flags),
-                                                        p(d["ws"]), p(d["info"]), st.cuda_stream), "cgp_factor_batched_dev")
-                    _lib.check(L.cgp_predict_factored_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), _lib.hptr(h),
-                                                          float(nugget), pflags, p(d["ws"]), p(d["info"]), p(g), None, self.M,
-                                                          p(d["new_y0"]), p(d["mean"]), p(d["var"]), st.cuda_stream),
-                               "cgp_predict_factored_dev")
-                else:
-                    _lib.check(L.cgp_predict_batched_dev(nb, p(d["off"]), self.N, self.dim, p(d["x"]), p(d["y"]), p(d["y0"]),
-                                                         p(d["y_err"]), _lib.hptr(h), float(nugget), float(floor), pflags,
-                                                         p(g), None, self.M, p(d["new_y0"]), p(d["mean"]), p(d["var"]),
-                                                         p(d["info"]), st.cuda_stream), "cgp_predict_batched_dev")
-                self.h["ll"][a:b].copy_(d["ll"][:nb], non_blocking=True)
-                self.h["mean"][a:b].copy_(d["mean"][:nb], non_blocking=True)
-                self.h["var"][a:b].copy_(d["var"][:nb], non_blocking=True)
-                self.h_info[a:b].copy_(d["info"][:nb], non_blocking=True)
-                self.d2h_bytes += nb * (8 + 16 * self.M + 4)
-        for st in self.streams:
-            st.synchronize()
-        ll = self.h["ll"].numpy()
-        total = float(np.add.accumulate(ll)[-1]) if self.B else 0.0
-        return total, ll, self.h["mean"].numpy(), self.h["var"].numpy(), self.h_info.numpy()
+        mean_fn = self._packed_mean if self.shared_mean else self.h["new_y0"]
+        total, up, down = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
+        rc = _lib.lib().cgp_streamer_run(self._handle, self.B, p(self.h["x"]), p(self.h["y"]), p(self.h["y0"]), p(self.h["y_err"]),
+                                         _lib.hptr(h), float(nugget), float(floor),
+                                         int(flags) | (_lib.CGP_MEAN_TEMPLATE if self.shared_mean else 0),
+                                         _lib.hptr(g), p(mean_fn), p(self.h["ll"]), p(self.h["mean"]), p(self.h["var"]),
+                                         p(self.h_info), C.byref(total), C.byref(up), C.byref(down))
+        _lib.check(rc, "cgp_streamer_run")
+        self.h2d_bytes, self.d2h_bytes = int(up.value), int(down.value)
+        return float(total.value), self.h["ll"].numpy(), self.h["mean"].numpy(), self.h["var"].numpy(), self.h_info.numpy()

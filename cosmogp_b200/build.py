@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcosmogp_b200.so")
-SOURCES = ["cgp_api.cu", "cgp_small.cu", "cgp_large.cu", "cgp_fit.cu"]
+SOURCES = ["cgp_api.cu", "cgp_small.cu", "cgp_large.cu", "cgp_fit.cu", "cgp_stream.cu"]
 HEADERS = [os.path.join(CSRC, "cgp_internal.h"), os.path.join(CSRC, "cgp_math.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "cosmogp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -19,7 +19,7 @@ static std::atomic<int64_t> g_launches{0};
 
 void count_launch(int n) { g_launches += n; }
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt);
   vsnprintf(g_err, sizeof g_err, fmt, ap);
   va_end(ap);

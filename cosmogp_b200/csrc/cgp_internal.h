@@ -139,4 +139,7 @@ int measure_fp64_peak(int kind, double* tflops);
 
 void count_launch(int n = 1);
 
+// records the message cgp_last_error() returns (thread-local) and hands back `code` (cgp_api.cu)
+int fail(int code, const char* fmt, ...);
+
 }  // namespace cgp

@@ -81,6 +81,26 @@ int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
                         const double* hyp, double nugget, double floor, unsigned flags,
                         double* ll_obj, int* info, double* ll_sum);
 
+/* ---- host-resident batches, pipelined.  A streamer owns n_streams CUDA streams and one set of device
+ *      buffers per stream for chunks of up to chunk_objects objects of EXACTLY n_pts points each and a
+ *      shared grid of m_grid points.  cgp_streamer_run cuts the batch into chunks and, per chunk and
+ *      stream: uploads the inputs, evaluates the log-likelihood (Gaussian_process.py:205-213) and the
+ *      prediction on the grid (:270-361) at the same hyperparameters, downloads ll / mean / var / info --
+ *      chunk k uploads while chunk k-1 computes and chunk k-2 downloads (PCIe is full duplex).  All
+ *      pointers are HOST pointers (page-locked memory is needed for the copies to overlap); y0, y_err,
+ *      new_y0 and var may be NULL; new_y0 is (n_obj, m_grid) or, with CGP_MEAN_TEMPLATE, [template | offsets].
+ *      ll_sum = ll[0] + ll[1] + ... in that order.  Returns the number of objects whose covariance was not
+ *      positive definite (their info[] != 0), or < 0.  h2d_bytes / d2h_bytes (may be NULL) count the copies. */
+typedef struct cgp_streamer cgp_streamer;
+int cgp_streamer_create(int64_t chunk_objects, int n_pts, int64_t m_grid, int dim, int n_streams, cgp_streamer** out);
+void cgp_streamer_destroy(cgp_streamer* s);
+int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
+                     const double* x, const double* y, const double* y0, const double* y_err,
+                     const double* hyp, double nugget, double floor, unsigned flags,
+                     const double* xnew, const double* new_y0,
+                     double* ll, double* mean, double* var, int* info, double* ll_sum,
+                     int64_t* h2d_bytes, int64_t* d2h_bytes);
+
 /* ---- per-object fits: one likelihood evaluation where object b uses its OWN hyperparameters
  *      hyp_obj[b*nh .. b*nh+nh) (nh = 2 or 4) and nugget_obj[b] (NULL -> the shared `nugget`).
  *      order (device, may be NULL) restricts the evaluation to n_active object ids; hyp_obj,

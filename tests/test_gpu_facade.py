@@ -158,7 +158,7 @@ def test_streamed_evaluator_matches_resident_batch(cg):
     m2, v2, _ = batch.predict([0.5, 2.0], 0.03, grid, new_y0=ny0)
     assert not info.any() and tot == t2
     assert np.array_equal(ll, ll2) and np.array_equal(mean, m2) and np.array_equal(var, v2)
-    assert ev.h2d_bytes == b * (4 * n + m) * 8 and ev.d2h_bytes == b * (8 + 16 * m + 4)
+    assert ev.h2d_bytes == (b * (4 * n + m) + m) * 8 and ev.d2h_bytes == b * (8 + 16 * m + 4)     # + the grid itself
     # shared mean (template + offset per object): same results from M + B mean values instead of B x M
     tmpl, diff = np.cos(grid / 5.0), rng.standard_normal(b)
     ev2 = StreamedEvaluator(b, n, m, n_chunks=7, shared_mean=True)
@@ -167,7 +167,20 @@ def test_streamed_evaluator_matches_resident_batch(cg):
     tot3, ll3, mean3, var3, info3 = ev2.run([0.5, 2.0], 0.03, grid)
     m4, v4, _ = batch.predict([0.5, 2.0], 0.03, grid, new_y0=tmpl[None, :] + diff[:, None])
     assert tot3 == t2 and np.array_equal(mean3, m4) and np.array_equal(var3, v4)
-    assert ev2.h2d_bytes == (b * (4 * n + 1) + 3 * m) * 8
+    assert ev2.h2d_bytes == (b * (4 * n + 1) + 3 * m + m) * 8                # template once per stream, grid once
+    # large chunks: ramped schedule (2048, 3276, ... up to the buffer capacity, then down again), two-kernel route
+    b, n, m = 40001, 20, 16
+    x = np.sort(rng.uniform(-10, 40, (b, n)), axis=1); y = rng.standard_normal((b, n)); ye = np.full((b, n), 0.2)
+    grid = np.linspace(-10, 40, m); tmpl, diff = np.cos(grid / 5.0), rng.standard_normal(b)
+    ev3 = StreamedEvaluator(b, n, m, n_chunks=4, n_streams=3, shared_mean=True)
+    for k, v in (("x", x), ("y", y), ("y0", 0.0), ("y_err", ye), ("template", tmpl), ("diff", diff)):
+        ev3.host(k)[...] = v
+    tot5, ll5, mean5, var5, info5 = ev3.run([0.5, 2.0], 0.03, grid)
+    big = DeviceBatch(x.ravel(), y.ravel(), np.arange(b + 1) * n, y_err=ye.ravel())
+    t6, ll6, _ = big.log_likelihood([0.5, 2.0], 0.03)
+    m6, v6, _ = big.predict([0.5, 2.0], 0.03, grid, mean_template=(tmpl, diff))
+    assert np.array_equal(ll5, ll6) and np.array_equal(mean5, m6) and np.array_equal(var5, v6) and not info5.any()
+    assert ev3.d2h_bytes == b * (8 + 16 * m + 4)
 
 
 def test_large_objects_through_the_facade(cg):
