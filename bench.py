@@ -252,6 +252,20 @@ def main():
     fa_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     pr_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
     clocks = sampler.stop()
+    # the same outputs from ONE factorisation per object (the factor kernel also emits the likelihood): what the
+    # end-to-end path runs; reported beside the step, whose separate LL launch is what a fit repeats ~60 times
+    def fused_step():
+        fac = batch.factor_dev(HYP, NUGGET, want_ll=True)
+        return batch.predict_factored_dev(fac, g_dev, None, ny0_dev, True, template_mean=True)
+    fused_step(); fused_step()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    f0.record()
+    for _ in range(max(3, min(args.steps, 10))):
+        fused_step()
+    f1.record()
+    torch.cuda.synchronize()
+    fused_ms = f0.elapsed_time(f1) / max(3, min(args.steps, 10))
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -260,9 +274,9 @@ def main():
     # ---- end to end through the numpy-in/numpy-out layer: every step uploads the step's inputs from
     # pinned host memory, runs LL + predict and downloads ll/mean/var; chunks of objects (ramping up from
     # 2048 to a quarter of the batch and down again) are pipelined: one upload stream, one download stream,
-    # kernels of consecutive chunks on 3 compute streams -- one native call per step (cgp_streamer_run)
+    # kernels of consecutive chunks on 6 compute streams -- one native call per step (cgp_streamer_run)
     from cosmogp_b200.batch import StreamedEvaluator
-    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "4")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "3")), shared_mean=True)
+    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "6")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "6")), shared_mean=True)
     for name, arr in (("x", x), ("y", y), ("y0", y0.reshape(B, N_EPOCH)), ("y_err", ye), ("template", tmpl), ("diff", d)):
         ev_e2e.host(name)[...] = arr
 
@@ -306,8 +320,13 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B, world),
         "clocks": clocks,
         "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "objects/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+                "path": "StreamedEvaluator.run -> cgp_streamer_run: pinned host in, pinned host out; per chunk one "
+                        "factorisation serves the likelihood and the prediction (the timed resident step above "
+                        "keeps the separate LL kernel)"},
         "gpu_launches": int(launches),
+        "fused_step": {"ms_per_step": fused_ms, "objects_per_s_per_gpu": B / (fused_ms * 1e-3),
+                       "what": "LL + predict from one factorisation per object (factor kernel emits LL), resident"},
         "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,PREDICT_F,8>: predictive mean+variance on the grid from the "
                      "TMA-staged factor (FP64 tensor pipe, DMMA.8x8x4)", "achieved": achieved,
                      "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": traffic,

@@ -47,7 +47,7 @@ SIGNATURES = {
     "cgp_predict_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "cgp_predict_batched_host": (_int, _BATCH + [_ptr] * 4 + _HYP + [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
     "cgp_factor_ws_doubles": (_i64, [_int]),
-    "cgp_factor_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_ptr, _ptr, _ptr]),
+    "cgp_factor_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_ptr, _ptr, _ptr, _ptr]),
     "cgp_predict_factored_dev": (_int, _BATCH_DEV + [_ptr, _ptr, _dbl, _u32, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
     "cgp_loo_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_int] + [_ptr] * 4 + [_ptr, _ptr]),
     "cgp_loo_batched_host": (_int, _BATCH + [_ptr] * 4 + _HYP + [_int] + [_ptr] * 4 + [_ptr]),

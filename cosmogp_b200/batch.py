@@ -250,20 +250,22 @@ class DeviceBatch:
         _lib.check(rc, "cgp_predict_batched_dev")
         return mean[:nout], (var[:nout] if want_var else None), self._info[:self.n_obj]
 
-    def factor_dev(self, hyp, nugget=0.0, floor=0.0, flags=0):
+    def factor_dev(self, hyp, nugget=0.0, floor=0.0, flags=0, want_ll=False):
         """Factorise every object once (objects of <= 64 points): returns an opaque device workspace
-        holding inv(L) and alpha, reusable by predict_factored_dev for any number of grids."""
+        holding inv(L) and alpha, reusable by predict_factored_dev for any number of grids.
+        want_ll: also return each object's log-likelihood (fac["ll"], device) from the same factorisation."""
         assert 0 < self.max_n <= 64, "factor_dev handles objects of 1..64 points"
         h = self._hyp(hyp)
         stride = int(_lib.lib().cgp_factor_ws_doubles(self.max_n))
         ws = torch.empty(max(self.n_obj, 1) * stride, dtype=torch.float64, device=self.device)
+        ll = torch.empty(max(self.n_obj, 1), dtype=torch.float64, device=self.device) if want_ll else None
         with torch.cuda.device(self.device):
             rc = _lib.lib().cgp_factor_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
                                                    self._p(self.y), self._p(self.y0), self._p(self.y_err), _lib.hptr(h),
-                                                   float(nugget), float(floor), int(flags), self._p(ws),
+                                                   float(nugget), float(floor), int(flags), self._p(ws), self._p(ll),
                                                    self._p(self._info), self._stream())
         _lib.check(rc, "cgp_factor_batched_dev")
-        return {"ws": ws, "hyp": h, "nugget": float(nugget), "flags": int(flags)}
+        return {"ws": ws, "hyp": h, "nugget": float(nugget), "flags": int(flags), "ll": None if ll is None else ll[:self.n_obj]}
 
     def predict_factored_dev(self, fac, grid, goff=None, new_y0=None, want_var=True, template_mean=False):
         """Prediction from a factor_dev() workspace; same outputs as predict_dev.  template_mean: new_y0 is

@@ -374,14 +374,14 @@ int64_t cgp_factor_ws_doubles(int max_n) {
 int cgp_factor_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
                            const double* x, const double* y, const double* y0, const double* y_err,
                            const double* hyp, double nugget, double floor, unsigned flags,
-                           double* ws, int* info, void* stream) {
+                           double* ws, double* ll_obj, int* info, void* stream) {
   if (n_obj < 0 || (n_obj && (!off || !x || !y || !ws || !info))) return fail(CGP_ERR_ARG, "cgp_factor_batched_dev: NULL argument");
   if (max_n <= 0 || max_n > 64) return fail(CGP_ERR_SIZE, "cgp_factor_batched_dev: objects of 1..64 points only (max_n = %d)", max_n);
   SmallArgs a; memset(&a, 0, sizeof a);
   int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
   if (rc) return rc;
   a.n_obj = n_obj; a.off = off; a.x = x; a.y = y; a.y0 = y0; a.yerr = y_err; a.info = info;
-  a.fws = ws; a.fws_stride = cgp_factor_ws_doubles(max_n); a.split = 1;
+  a.fws = ws; a.fws_stride = cgp_factor_ws_doubles(max_n); a.split = 1; a.ll = ll_obj;
   return run_small(TASK_FACTOR, dim, max_n, a, (cudaStream_t)stream, "cgp_factor_batched_dev");
 }
 

@@ -292,7 +292,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         diag_factor(s0[0], s1[0], L, t0, t1, piv, badk);
         double* p = tiles + slot(J, J) * TILE;
         p[L.st0] = t0; p[L.st1] = t1;
-        if (TASK == TASK_LL) {
+        if (TASK == TASK_LL || TASK == TASK_FACTOR) {
           lp_m *= piv;
           const int hi = __double2hiint(lp_m);
           const int e = ((hi >> 20) & 0x7ff) - 1023;
@@ -432,6 +432,16 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     }   // TASK != TASK_PREDICT_F
 
     if (TASK == TASK_FACTOR) {
+      if (a.ll) {                                        // the likelihood comes for free: z and the pivots are here
+        double quad = 0.0;
+#pragma unroll
+        for (int i0 = 0; i0 < LD; i0 += 32) { const int i = i0 + lane; if (i < LD) quad = fma(vz[i], vz[i], quad); }
+        quad = red_g(red_t(quad));
+        if (lane == 0) {
+          const double logdet = log(lp_m) + (double)lp_e * LN2;
+          a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+        }
+      }
       // ---------------- spill the factor (L^-1 tiles, alpha) for the prediction kernel: 512-byte rows
       double* dst = a.fws + b * a.fws_stride;
 #pragma unroll 4

@@ -214,13 +214,16 @@ int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
     const double* dye = y_err ? k.ye : nullptr;
     const double* dny0 = (m && new_y0) ? k.ny0 : nullptr;
     double* dvar = var ? k.var : nullptr;
-    rc = cgp_ll_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, kflags,
-                            k.ll, k.info, cs);
-    if (rc < 0) break;
+    const bool fused_ll = m && s->two_kernel;        // the factor kernel emits the likelihood too: one factorisation
+    if (!fused_ll) {
+      rc = cgp_ll_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, kflags,
+                              k.ll, k.info, cs);
+      if (rc < 0) break;
+    }
     if (m) {
       if (s->two_kernel) {
         rc = cgp_factor_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, kflags,
-                                    k.ws, k.info, cs);
+                                    k.ws, k.ll, k.info, cs);
         if (rc < 0) break;
         rc = cgp_predict_factored_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, hyp, nugget, flags, k.ws, k.info,
                                       s->grid, nullptr, (int64_t)m, dny0, k.mean, dvar, cs);

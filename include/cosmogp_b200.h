@@ -163,12 +163,14 @@ int cgp_predict_batched_host(int64_t n_obj, const int64_t* off, int dim,
  *      cgp_predict_batched_dev as separate calls.  ws holds, per object, inv(L) as 8x8 tiles in DMMA
  *      fragment order followed by alpha = K^-1 (y - y0): cgp_factor_ws_doubles(max_n) doubles each.
  *      cgp_predict_factored_dev stages each object's factor into shared memory with one TMA bulk
- *      copy; var may be NULL.  hyp / nugget / flags must be those used for the factorisation. */
+ *      copy; var may be NULL.  hyp / nugget / flags must be those used for the factorisation.
+ *      ll_obj (may be NULL) receives each object's log-likelihood (Gaussian_process.py:13-75) from the
+ *      same factorisation: an evaluation of LL and prediction at the same hyperparameters factorises once. */
 int64_t cgp_factor_ws_doubles(int max_n);
 int cgp_factor_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
                            const double* x, const double* y, const double* y0, const double* y_err,
                            const double* hyp, double nugget, double floor, unsigned flags,
-                           double* ws, int* info, void* stream);
+                           double* ws, double* ll_obj, int* info, void* stream);
 int cgp_predict_factored_dev(int64_t n_obj, const int64_t* off, int max_n, int dim, const double* x,
                              const double* hyp, double nugget, unsigned flags, const double* ws, const int* info,
                              const double* xnew, const int64_t* goff, int64_t m_shared,

@@ -348,7 +348,12 @@ def test_factor_once_predict_many(L):
     y0 = 0.1 * rng.standard_normal((b, n))
     hyp, nug = [0.6, 2.5], 0.04
     batch = DeviceBatch(x.ravel(), y.ravel(), np.arange(b + 1, dtype=np.int64) * n, y0=y0.ravel(), y_err=ye.ravel())
-    fac = batch.factor_dev(hyp, nug)
+    fac = batch.factor_dev(hyp, nug, want_ll=True)
+    ll_fac = fac["ll"].cpu().numpy()                    # the likelihood from the same factorisation
+    _, ll_ref, _ = batch.log_likelihood(hyp, nug)
+    assert_close(ll_fac, ll_ref, 1e-13, 1e-11)
+    for i in (0, 1234, 2999):
+        assert_close(ll_fac[i], O.log_likelihood(y[i], x[i], hyp, nug, ye[i], y0[i]), RTOL)
     for m in (37, 100):
         grid = np.linspace(-12, 42, m); ny0 = rng.standard_normal((b, m))
         mean, var, info = batch.predict_factored_dev(fac, torch.from_numpy(grid).cuda(), None, torch.from_numpy(ny0).cuda(), True)
