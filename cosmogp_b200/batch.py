@@ -308,30 +308,39 @@ class DeviceBatch:
             var_h = var_h.reshape(self.n_obj, m) if want_var else None
         return mean_h, var_h, info_h
 
-    def loo(self, hyp, nugget, mean=None, mode=_lib.CGP_LOO_PLAIN, floor=0.0, flags=0):
+    def loo_dev(self, hyp, nugget, mean=None, mode=_lib.CGP_LOO_PLAIN, floor=0.0, flags=0):
         """Closed-form leave-one-out; `mean` (flat, host) replaces the batch's y0 when given.
-        -> pred, pred_var, pull, resid (flat host arrays), info."""
+        -> pred, pred_var, pull, resid (flat DEVICE tensors), info (device)."""
         m = self._up(np.asarray(mean, dtype=np.float64)) if mean is not None else self.y0
         outs = [torch.empty(max(self.n_pts, 1), dtype=torch.float64, device=self.device) for _ in range(4)]
         oh = self._objhyp(hyp, nugget)
-        if oh is not None:
-            with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device):
+            if oh is not None:
                 rc = _lib.lib().cgp_loo_objhyp_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
                                                    self._p(self.y), self._p(m), self._p(self.y_err), self._p(oh[0]),
                                                    self._p(oh[1]), oh[2], float(floor), int(flags), int(mode),
                                                    *[self._p(o) for o in outs], self._p(self._info), self._stream())
-            _lib.check(rc, "cgp_loo_objhyp_dev")
-            res = [self._down(o[:self.n_pts]) for o in outs]
-            return res + [self._down(self._info[:self.n_obj])]
-        h = self._hyp(hyp)
+            else:
+                h = self._hyp(hyp)
+                rc = _lib.lib().cgp_loo_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                                    self._p(self.y), self._p(m), self._p(self.y_err), _lib.hptr(h),
+                                                    float(nugget), float(floor), int(flags), int(mode),
+                                                    *[self._p(o) for o in outs], self._p(self._info), self._stream())
+        _lib.check(rc, "cgp_loo_objhyp_dev" if oh is not None else "cgp_loo_batched_dev")
+        return [o[:self.n_pts] for o in outs] + [self._info[:self.n_obj]]
+
+    def loo(self, hyp, nugget, mean=None, mode=_lib.CGP_LOO_PLAIN, floor=0.0, flags=0):
+        """loo_dev with the results brought to the host: pred, pred_var, pull, resid (flat), info."""
+        return [self._down(t) for t in self.loo_dev(hyp, nugget, mean, mode, floor, flags)]
+
+    def moments(self, v, center=0.0):
+        """(sum (v - center), sum (v - center)^2) of a device tensor, reduced on the device (cgp_moments_dev)."""
+        out = torch.empty(2, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            rc = _lib.lib().cgp_loo_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
-                                                self._p(self.y), self._p(m), self._p(self.y_err), _lib.hptr(h),
-                                                float(nugget), float(floor), int(flags), int(mode),
-                                                *[self._p(o) for o in outs], self._p(self._info), self._stream())
-        _lib.check(rc, "cgp_loo_batched_dev")
-        res = [self._down(o[:self.n_pts]) for o in outs]
-        return res + [self._down(self._info[:self.n_obj])]
+            _lib.check(_lib.lib().cgp_moments_dev(self._p(v), int(v.numel()), float(center), self._p(out), self._stream()),
+                       "cgp_moments_dev")
+        s1, s2 = out.cpu().tolist()
+        return s1, s2
 
     def matrices(self, hyp, nugget, want_k=True, want_kinv=True, floor=0.0, flags=0):
         """kernel_matrix / inv_kernel_matrix per object (lists of (N,N) host arrays)."""

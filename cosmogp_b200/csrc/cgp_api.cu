@@ -558,6 +558,12 @@ int cgp_trsm_rows_dev(const double* a, int64_t n_pad, int64_t ld, double* v, int
   return e ? cuda_fail(e, "cgp_trsm_rows_dev") : 0;
 }
 
+int cgp_moments_dev(const double* v, int64_t n, double center, double* out2, void* stream) {
+  if (n < 0 || (n && !v) || !out2) return fail(CGP_ERR_ARG, "cgp_moments_dev: NULL argument");
+  int e = large_moments(v, n, center, out2, (cudaStream_t)stream);
+  return e ? cuda_fail(e, "cgp_moments_dev") : 0;
+}
+
 int cgp_gemm_nt_dev(const double* a, int64_t lda, const double* b, int64_t ldb, double* c, int64_t ldc,
                     int64_t m, int64_t n, int64_t k, double alpha, double beta, int lower_only, void* stream) {
   if (!a || !b || !c) return fail(CGP_ERR_ARG, "cgp_gemm_nt_dev: NULL argument");

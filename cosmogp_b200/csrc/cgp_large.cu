@@ -315,6 +315,55 @@ __global__ void sum_kernel(const double* v, int64_t n, double* out) {         //
     if (threadIdx.x == 0) out[0] = acc;
   }
 }
+// Centred moments of a long vector, for scipy.stats.norm.fit of the pulls (cosmogp/pull.py:102) without a
+// download: partial[2*blk] = sum (v - c), partial[2*blk+1] = sum (v - c)^2 over the block's contiguous
+// segment (16-byte loads, HBM bound); a second one-CTA pass adds the partials in a fixed order.
+__global__ void __launch_bounds__(256) moments_partial_kernel(const double* __restrict__ v, int64_t n, double c,
+                                                              double* __restrict__ partial) {
+  __shared__ double s1[8], s2[8];
+  const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 1) & ~(int64_t)1;      // even: segments stay 16-byte aligned
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+  double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+  const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+  int64_t i = lo + 2 * (int64_t)threadIdx.x;
+  if (aligned) {
+    for (; i + 1 < hi; i += 2 * blockDim.x) {
+      const double2 w = *reinterpret_cast<const double2*>(v + i);
+      const double d0 = w.x - c, d1 = w.y - c;
+      a1 += d0; a2 = fma(d0, d0, a2); b1 += d1; b2 = fma(d1, d1, b2);
+    }
+    if (i < hi) { const double d0 = v[i] - c; a1 += d0; a2 = fma(d0, d0, a2); }
+  } else {
+    for (; i < hi; i += 2 * blockDim.x) {
+      const double d0 = v[i] - c; a1 += d0; a2 = fma(d0, d0, a2);
+      if (i + 1 < hi) { const double d1 = v[i + 1] - c; b1 += d1; b2 = fma(d1, d1, b2); }
+    }
+  }
+  a1 += b1; a2 += b2;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a1; s2[threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int w = 0; w < 8; ++w) { t1 += s1[w]; t2 += s2[w]; }
+    partial[2 * blockIdx.x] = t1; partial[2 * blockIdx.x + 1] = t2;
+  }
+}
+__global__ void moments_final_kernel(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
+  __shared__ double s1[32], s2[32];
+  double a1 = 0.0, a2 = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) { a1 += partial[2 * i]; a2 += partial[2 * i + 1]; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a1; s2[threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t1 += s1[w]; t2 += s2[w]; }
+    out[0] = t1; out[1] = t2;
+  }
+}
 __global__ void potrf_setup_kernel(int64_t* blk_off, int64_t* blk_aoff, int nblk, int64_t ld) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k == 0) { blk_off[0] = 0; blk_off[1] = 128; }
@@ -561,6 +610,17 @@ int large_row_var(const double* v, int64_t ldv, int64_t n_pad, int64_t rows, dou
 }
 int large_dot_sq(const double* v, int64_t n, double* out, cudaStream_t st) {
   dot_sq_kernel<<<1, 1024, 0, st>>>(v, n, out); count_launch(); return (int)cudaGetLastError();
+}
+int large_moments(const double* v, int64_t n, double center, double* out2, cudaStream_t st) {
+  const int nblk = n < (int64_t)1 << 16 ? 1 : 148 * 8;
+  double* partial = nullptr;
+  cudaError_t ce = cudaMallocAsync((void**)&partial, sizeof(double) * 2 * nblk, st);
+  if (ce != cudaSuccess) return (int)ce;
+  moments_partial_kernel<<<nblk, 256, 0, st>>>(v, n, center, partial);
+  moments_final_kernel<<<1, 256, 0, st>>>(partial, nblk, out2);
+  count_launch(2);
+  cudaFreeAsync(partial, st);
+  return (int)cudaGetLastError();
 }
 int large_sum(const double* v, int64_t n, double* out, cudaStream_t st) {
   sum_kernel<<<1, 1024, 0, st>>>(v, n, out); count_launch(); return (int)cudaGetLastError();

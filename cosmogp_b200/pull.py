@@ -32,11 +32,10 @@ class build_pull:
 
         self.n_object = len(y)
 
-        empty = np.zeros(1, dtype=np.int64)
-        self._pull = RaggedView(np.zeros(0), empty)       # per object, list-like (views, no 10^6-element list)
-        self.pull = np.zeros(0)          # flat, grows with every compute_pull call like the reference lists
-        self.residual = np.zeros(0)
-        self.prediction = RaggedView(np.zeros(0), empty)
+        # results stay on the device until somebody reads them: one entry per compute_pull call
+        # (the reference's lists grow with every call); see the properties below
+        self._results = []
+        self._host = {}
 
         self.pull_average = None
         self.pull_std = None
@@ -71,20 +70,64 @@ class build_pull:
                 template = template + np.repeat(np.asarray(diff, dtype=float), np.diff(off))
 
         batch = DeviceBatch(x_flat, y_flat, off, y0=template, y_err=ye_flat, dim=dim)
-        pred, pvar, pull, resid, info = batch.loo(self.hyperparameters, self.nugget, mode=mode, flags=self.flags)
-        bad = np.nonzero(info)[0]
+        pred, pvar, pull, resid, info = batch.loo_dev(self.hyperparameters, self.nugget, mode=mode, flags=self.flags)
+        bad = np.nonzero(batch._down(info))[0]
         if len(bad):
             raise np.linalg.LinAlgError("covariance of object %d is not positive definite" % int(bad[0]))
+        self._results.append({"batch": batch, "off": off, "pull": pull, "residual": resid, "prediction": pred,
+                              "prediction_variance": pvar})
+        self._host = {}
 
-        self._pull = self._pull.extended(pull, off)
-        self.prediction = self.prediction.extended(pred, off)
-        self.prediction_variance = pvar
-        self.pull = pull if not len(self.pull) else np.concatenate([self.pull, pull])
-        self.residual = resid if not len(self.residual) else np.concatenate([self.residual, resid])
+        # scipy.stats.norm.fit (pull.py:102) = sample mean and population standard deviation, over every pull
+        # computed so far; reduced on the device (two passes: the mean, then the spread about it)
+        n_tot = sum(int(r["pull"].numel()) for r in self._results)
+        if n_tot:
+            total = sum(r["batch"].moments(r["pull"], 0.0)[0] for r in self._results)
+            self.pull_average = total / n_tot
+            parts = [r["batch"].moments(r["pull"], self.pull_average) for r in self._results]
+            self.pull_average += sum(p[0] for p in parts) / n_tot          # second-pass correction of the mean
+            self.pull_std = float(np.sqrt(sum(p[1] for p in parts) / n_tot
+                                          - (sum(p[0] for p in parts) / n_tot) ** 2))
+        else:
+            self.pull_average = self.pull_std = float("nan")
 
-        # scipy.stats.norm.fit (pull.py:102) = sample mean and population standard deviation
-        self.pull_average = float(np.mean(self.pull))
-        self.pull_std = float(np.sqrt(np.mean((self.pull - self.pull_average) ** 2)))
+    # ---- results, brought to the host when read (10^6 x 40 pulls are 320 MB per array)
+    def _flat(self, name):
+        if name not in self._host:
+            parts = [r["batch"]._down(r[name]) for r in self._results]
+            self._host[name] = parts[0] if len(parts) == 1 else (np.concatenate(parts) if parts else np.zeros(0))
+        return self._host[name]
+
+    def _offsets(self):
+        off = np.zeros(1, dtype=np.int64)
+        for r in self._results:
+            off = np.concatenate([off, off[-1] + r["off"][1:]])
+        return off
+
+    @property
+    def pull(self):
+        """flat array of all pulls, grows with every compute_pull call like the reference list"""
+        return self._flat("pull")
+
+    @property
+    def residual(self):
+        return self._flat("residual")
+
+    @property
+    def _pull(self):
+        """per object, list-like (views, no 10^6-element list)"""
+        return RaggedView(self._flat("pull"), self._offsets())
+
+    @property
+    def prediction(self):
+        return RaggedView(self._flat("prediction"), self._offsets())
+
+    @property
+    def prediction_variance(self):
+        """|cov_tt| of the most recent compute_pull call"""
+        if not self._results:
+            return None
+        return self._results[-1]["batch"]._down(self._results[-1]["prediction_variance"])
 
     def plot_result(self, binning=60):
         """Histogram of the pulls with the fitted normal law (pull.py:105-140)."""

@@ -239,6 +239,12 @@ int cgp_large_predict_dev(const double* a, int64_t n, int64_t n_pad, int64_t ld,
 /* v_m = L^-1 h_m for `rows` rows of V (rows x n_pad, rows % 128 == 0), in place. */
 int cgp_trsm_rows_dev(const double* a, int64_t n_pad, int64_t ld, double* v, int64_t ldv, int64_t rows, void* stream);
 
+/* Centred moments of a device vector: out2[0] = sum (v[i] - center), out2[1] = sum (v[i] - center)^2
+ * (out2: 2 doubles on the device; fixed summation order, reproducible).  Two calls give what
+ * scipy.stats.norm.fit(pull) returns at cosmogp/pull.py:102 (mean, then the population standard
+ * deviation about it) without bringing 10^6 x N pulls to the host. */
+int cgp_moments_dev(const double* v, int64_t n, double center, double* out2, void* stream);
+
 /* C[m x n] = beta C + alpha A[m x k] B[n x k]^T on the FP64 tensor pipe; m, n % 128 == 0, k % 16 == 0;
  * lower_only != 0 computes only the tiles on or below the block diagonal. */
 int cgp_gemm_nt_dev(const double* a, int64_t lda, const double* b, int64_t ldb, double* c, int64_t ldc,

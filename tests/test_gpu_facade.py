@@ -114,6 +114,28 @@ def test_build_pull_modes(cg):
     bc = cg.build_pull(ys, xs, r["hyp"], nugget=0.05, y_err=yes, y_mean=r["mean_y"], x_axis_mean=r["mean_x"])
     bc.compute_pull(diff=list(r["diff"]), svd_method=False)
     assert_close(bc.pull, r["pullC"], 1e-8, 1e-11)
+    # the reference's lists grow with every compute_pull call (pull.py:94-102): the normal law is refitted on all of them
+    bc.compute_pull(svd_method=False)
+    assert len(bc.pull) == 2 * len(r["pullC"]) and len(bc._pull) == 2 * len(ys) and len(bc.prediction) == 2 * len(ys)
+    assert_close(bc.pull[len(r["pullC"]):], r["pullB"], 1e-8, 1e-11)
+    both = np.concatenate([r["pullC"], r["pullB"]])
+    assert_close([bc.pull_average, bc.pull_std], [np.mean(both), np.std(both)], 1e-8)
+    assert_close(bc._pull[len(ys) + 1], split(r["pullB"], off)[1], 1e-8, 1e-11)
+
+
+def test_moments_on_device(cg):
+    """cgp_moments_dev (the norm.fit of the pulls without a download) against numpy, any size and alignment."""
+    import torch
+    from cosmogp_b200.batch import DeviceBatch
+    rng = np.random.default_rng(2)
+    b = DeviceBatch(np.arange(4.0), np.arange(4.0), np.array([0, 4]))
+    for n in (1, 2, 3, 255, 4097, 65536, 1000003):
+        v = rng.standard_normal(n + 1) * 3.0 + 0.7
+        d = torch.from_numpy(v).cuda()
+        for view, ref in ((d[:n], v[:n]), (d[1:], v[1:])):          # second view: only 8-byte aligned
+            s1, s2 = b.moments(view, 0.25)
+            assert_close(s1, np.sum(ref - 0.25), 1e-11, 1e-9); assert_close(s2, np.sum((ref - 0.25) ** 2), 1e-12)
+    assert b.moments(torch.zeros(0, dtype=torch.float64, device="cuda"), 1.0) == (0.0, 0.0)
 
 
 def test_2d_objects(cg):
