@@ -216,7 +216,7 @@ def main():
         # for large batches; called as two entry points here so that each kernel is timed on its own)
         fac = batch.factor_dev(HYP, NUGGET)
         e_mid2.record()
-        mean, var, _ = batch.predict_factored_dev(fac, g_dev, None, ny0_dev, True, template_mean=True)
+        mean, var, _ = batch.predict_factored_dev(fac, g_dev, None, ny0_dev, True, template_mean=True, uniform_grid=True)
         return ll, mean, var
 
     e_mid = torch.cuda.Event(enable_timing=True)
@@ -256,7 +256,7 @@ def main():
     # end-to-end path runs; reported beside the step, whose separate LL launch is what a fit repeats ~60 times
     def fused_step():
         fac = batch.factor_dev(HYP, NUGGET, want_ll=True)
-        return batch.predict_factored_dev(fac, g_dev, None, ny0_dev, True, template_mean=True)
+        return batch.predict_factored_dev(fac, g_dev, None, ny0_dev, True, template_mean=True, uniform_grid=True)
     fused_step(); fused_step()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()

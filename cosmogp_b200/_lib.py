@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcosmogp_b200.so")
 
 CGP_AMP_ON_AUTOCOV = 1
 CGP_MEAN_TEMPLATE = 2
+CGP_GRID_UNIFORM = 4
 CGP_SMALL_MAX_N = 224
 CGP_LOO_PLAIN = 0
 CGP_LOO_RECENTER = 1

@@ -267,9 +267,10 @@ class DeviceBatch:
         _lib.check(rc, "cgp_factor_batched_dev")
         return {"ws": ws, "hyp": h, "nugget": float(nugget), "flags": int(flags), "ll": None if ll is None else ll[:self.n_obj]}
 
-    def predict_factored_dev(self, fac, grid, goff=None, new_y0=None, want_var=True, template_mean=False):
+    def predict_factored_dev(self, fac, grid, goff=None, new_y0=None, want_var=True, template_mean=False, uniform_grid=False):
         """Prediction from a factor_dev() workspace; same outputs as predict_dev.  template_mean: new_y0 is
-        the packed shared mean [template on the grid (M) | per-object offsets (B)] (CGP_MEAN_TEMPLATE)."""
+        the packed shared mean [template on the grid (M) | per-object offsets (B)] (CGP_MEAN_TEMPLATE).
+        uniform_grid: hint that the shared 1D grid is uniformly spaced (CGP_GRID_UNIFORM; verified by the library)."""
         m = 0 if goff is not None else int(grid.shape[0])
         nout = int(goff[-1].item()) if goff is not None else self.n_obj * m
         mean = torch.empty(max(nout, 1), dtype=torch.float64, device=self.device)
@@ -277,7 +278,8 @@ class DeviceBatch:
         with torch.cuda.device(self.device):
             rc = _lib.lib().cgp_predict_factored_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
                                                      _lib.hptr(fac["hyp"]), fac["nugget"],
-                                                     fac["flags"] | (_lib.CGP_MEAN_TEMPLATE if template_mean else 0), self._p(fac["ws"]),
+                                                     fac["flags"] | (_lib.CGP_MEAN_TEMPLATE if template_mean else 0)
+                                                     | (_lib.CGP_GRID_UNIFORM if uniform_grid else 0), self._p(fac["ws"]),
                                                      self._p(self._info), self._p(grid), self._p(goff), m,
                                                      self._p(new_y0), self._p(mean), self._p(var), self._stream())
         _lib.check(rc, "cgp_predict_factored_dev")
@@ -298,6 +300,8 @@ class DeviceBatch:
             assert packed.size == int(g.shape[0]) + self.n_obj, "template must cover the grid, offsets the objects"
             new_y0, flags = packed, int(flags) | _lib.CGP_MEAN_TEMPLATE
         ny0 = self._up(np.asarray(new_y0, dtype=np.float64)) if new_y0 is not None else None
+        if goff is None and self.dim == 1:
+            flags = int(flags) | _lib.CGP_GRID_UNIFORM          # a hint; the library checks the grid and the length scale
         mean, var, info = self.predict_dev(hyp, nugget, g, go, ny0, want_var, floor, flags)
         mean_h = self._down(mean)
         var_h = self._down(var) if want_var else None
@@ -427,7 +431,7 @@ class StreamedEvaluator:
         total, up, down = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
         rc = _lib.lib().cgp_streamer_run(self._handle, self.B, p(self.h["x"]), p(self.h["y"]), p(self.h["y0"]), p(self.h["y_err"]),
                                          _lib.hptr(h), float(nugget), float(floor),
-                                         int(flags) | (_lib.CGP_MEAN_TEMPLATE if self.shared_mean else 0),
+                                         int(flags) | (_lib.CGP_MEAN_TEMPLATE if self.shared_mean else 0) | _lib.CGP_GRID_UNIFORM,
                                          _lib.hptr(g), p(mean_fn), p(self.h["ll"]), p(self.h["mean"]), p(self.h["var"]),
                                          p(self.h_info), C.byref(total), C.byref(up), C.byref(down))
         _lib.check(rc, "cgp_streamer_run")

@@ -66,6 +66,29 @@ static int run_small(Task task, int dim, int max_n, SmallArgs& a, cudaStream_t s
   return 0;
 }
 
+// CGP_GRID_UNIFORM is a hint: the recurrence kernel (TASK_PREDICT_FU) runs only if the shared 1D grid really is
+// g0 + j*delta to within a few ulp and the length scale is at least one spacing (see cgp_small64.cu).
+// `grid` is a host copy.  Returns 1 when the fast path applies.
+int uniform_grid_ok(const double* grid, int64_t m, const double* hyp) {
+  if (!grid || !hyp || m < 2) return 0;
+  const double g0 = grid[0], delta = (grid[m - 1] - g0) / (double)(m - 1);
+  const double l = std::fabs(hyp[1]);
+  if (!(delta != 0.0) || !std::isfinite(delta) || !std::isfinite(g0) || !(l >= std::fabs(delta))) return 0;
+  double gmax = std::fabs(g0) > std::fabs(grid[m - 1]) ? std::fabs(g0) : std::fabs(grid[m - 1]);
+  const double tol = 4.0 * 2.220446049250313e-16 * (gmax > 0.0 ? gmax : 1.0);
+  for (int64_t j = 0; j < m; ++j)
+    if (!(std::fabs(grid[j] - std::fma((double)j, delta, g0)) <= tol)) return 0;
+  return 1;
+}
+static int uniform_grid_ok_dev(const double* xnew_dev, int64_t m, const double* hyp, cudaStream_t st) {
+  if (m < 2 || m > (int64_t)1 << 24) return 0;
+  std::vector<double> g((size_t)m);
+  cudaError_t e = cudaMemcpyAsync(g.data(), xnew_dev, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return uniform_grid_ok(g.data(), m, hyp);
+}
+
 // ---- tiny RAII helpers for the _host entry points ------------------------------------
 struct DevBuf {
   void* p = nullptr; cudaStream_t st;
@@ -285,6 +308,7 @@ static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
     const int64_t stride = factor_ws_doubles(nb);
     const int64_t chunk = 65536;
     double* ws = nullptr;
+    const bool uniform = (flags & CGP_GRID_UNIFORM) && dim == 1 && !goff && !hyp_obj && uniform_grid_ok_dev(xnew, m_shared, hyp, st);
     keep_pool_memory();
     cudaError_t ce = cudaMallocAsync((void**)&ws, (size_t)((n_obj < chunk ? n_obj : chunk) * stride) * sizeof(double), st);
     if (ce != cudaSuccess) return cuda_fail((int)ce, "cgp_predict_batched_dev (workspace)");
@@ -302,7 +326,7 @@ static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
       f.fws = ws; f.fws_stride = stride;
       if (hyp_obj) { f.hyp_obj = hyp_obj + c0 * f.n_hyp; if (nugget_obj) f.nugget_obj = nugget_obj + c0; }
       rc2 = run_small(TASK_FACTOR, dim, max_n, f, st, "cgp_predict_batched_dev (factor)");
-      if (!rc2) rc2 = run_small(TASK_PREDICT_F, dim, max_n, f, st, "cgp_predict_batched_dev (predict)");
+      if (!rc2) rc2 = run_small(uniform ? TASK_PREDICT_FU : TASK_PREDICT_F, dim, max_n, f, st, "cgp_predict_batched_dev (predict)");
     }
     cudaFreeAsync(ws, st);
     return rc2;
@@ -389,6 +413,20 @@ int cgp_predict_factored_dev(int64_t n_obj, const int64_t* off, int max_n, int d
                              const double* hyp, double nugget, unsigned flags, const double* ws, const int* info,
                              const double* xnew, const int64_t* goff, int64_t m_shared,
                              const double* new_y0, double* mean, double* var, void* stream) {
+  int uniform = 0;
+  if ((flags & CGP_GRID_UNIFORM) && dim == 1 && !goff && xnew && hyp && n_obj > 0)
+    uniform = uniform_grid_ok_dev(xnew, m_shared, hyp, (cudaStream_t)stream);
+  return cgp::predict_factored(n_obj, off, max_n, dim, x, hyp, nugget, flags, ws, info, xnew, goff, m_shared, new_y0, mean, var,
+                               uniform, stream);
+}
+
+}  // extern "C"
+
+// uniform: 1 = the caller has verified the grid on the host (uniform_grid_ok), 0 = general kernel
+int cgp::predict_factored(int64_t n_obj, const int64_t* off, int max_n, int dim, const double* x,
+                          const double* hyp, double nugget, unsigned flags, const double* ws, const int* info,
+                          const double* xnew, const int64_t* goff, int64_t m_shared,
+                          const double* new_y0, double* mean, double* var, int uniform, void* stream) {
   if (n_obj < 0 || (n_obj && (!off || !x || !ws || !info || !xnew || !mean)))
     return fail(CGP_ERR_ARG, "cgp_predict_factored_dev: NULL argument");
   if (max_n <= 0 || max_n > 64) return fail(CGP_ERR_SIZE, "cgp_predict_factored_dev: objects of 1..64 points only (max_n = %d)", max_n);
@@ -410,8 +448,11 @@ int cgp_predict_factored_dev(int64_t n_obj, const int64_t* off, int max_n, int d
     if (want > 1) split = (int)want;
   }
   a.split = split;
-  return run_small(TASK_PREDICT_F, dim, max_n, a, (cudaStream_t)stream, "cgp_predict_factored_dev");
+  const bool fu = uniform && dim == 1 && !goff && m_shared >= 2;
+  return run_small(fu ? TASK_PREDICT_FU : TASK_PREDICT_F, dim, max_n, a, (cudaStream_t)stream, "cgp_predict_factored_dev");
 }
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------ LOO
 static int loo_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,

@@ -19,6 +19,7 @@ struct Cov {
 
 #define CGP_FLAG_AMP_ON_AUTOCOV 1u
 #define CGP_FLAG_MEAN_TEMPLATE 2u
+#define CGP_FLAG_GRID_UNIFORM 4u
 
 // hyp -> Cov (cosmogp/kernel.py:71-75 for 1D, :127-151 for 2D); shared by the host API and by the
 // kernels when every object carries its own hyperparameters.  A singular / NaN metric propagates.
@@ -42,7 +43,8 @@ __host__ __device__ inline Cov cov_from_hyp(int dim, const double* hyp, double n
 
 // TASK_FACTOR writes L^-1 (fragment-order tiles) + alpha per object to a workspace; TASK_PREDICT_F
 // predicts from that workspace (staged into shared memory by one TMA bulk copy per object).
-enum Task { TASK_LL = 0, TASK_PREDICT = 1, TASK_LOO = 2, TASK_MATRICES = 3, TASK_FACTOR = 4, TASK_PREDICT_F = 5 };
+// TASK_PREDICT_FU: TASK_PREDICT_F for dim 1 on a uniformly spaced shared grid with l >= spacing (exps by recurrence).
+enum Task { TASK_LL = 0, TASK_PREDICT = 1, TASK_LOO = 2, TASK_MATRICES = 3, TASK_FACTOR = 4, TASK_PREDICT_F = 5, TASK_PREDICT_FU = 6 };
 
 struct SmallArgs {
   int64_t n_obj;
@@ -125,6 +127,7 @@ int launch_small64_d1_t4(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d1_t5(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d2_t4(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d2_t5(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d1_t6(int nb, const SmallArgs& a, cudaStream_t stream);
 // doubles per object in the factor workspace for nb blocks of 8 points
 inline int64_t factor_ws_doubles(int nb) { return (int64_t)(nb * (nb + 1) / 2) * 64 + 8 * nb; }
 
@@ -139,6 +142,14 @@ int fit_nelder_mead(int64_t n_obj, const int64_t* off, int max_n, int dim,
 int measure_fp64_peak(int kind, double* tflops);
 
 void count_launch(int n = 1);
+
+// uniform-grid fast path of the factored prediction (cgp_api.cu): the check on a host copy of the grid, and the
+// entry point that trusts it (cgp_predict_factored_dev verifies by reading the grid back from the device)
+int uniform_grid_ok(const double* grid_host, int64_t m, const double* hyp);
+int predict_factored(int64_t n_obj, const int64_t* off, int max_n, int dim, const double* x,
+                     const double* hyp, double nugget, unsigned flags, const double* ws, const int* info,
+                     const double* xnew, const int64_t* goff, int64_t m_shared,
+                     const double* new_y0, double* mean, double* var, int uniform, void* stream);
 
 // records the message cgp_last_error() returns (thread-local) and hands back `code` (cgp_api.cu)
 int fail(int code, const char* fmt, ...);

@@ -119,7 +119,7 @@ constexpr int n_vec64(int task) { return task == TASK_LOO ? 6 : 1; }
 // registers per thread (grid phase: 64 accumulators + 32 fragments), 4 warps <= 128 (factorisation,
 // pulls: shared memory allows 16+ objects per SM below 56 points); hence the minimum-blocks bounds.
 template <int DIM, int TASK, int NB>
-__global__ void __launch_bounds__(32, (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) ? 12 : 16)
+__global__ void __launch_bounds__(32, (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU) ? 12 : 16)
 gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
@@ -132,20 +132,22 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   double* noise = px + DIM * LD;
   double* vr = noise + LD;                 // r (LL: becomes z)
   // predict: z overwrites the (dead) noise vector and alpha overwrites r -> same footprint as LL
-  constexpr bool PRED_LIKE = TASK == TASK_PREDICT || TASK == TASK_FACTOR || TASK == TASK_PREDICT_F;
+  constexpr bool PF = TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU;      // predict from a stored factor
+  constexpr bool UNI = TASK == TASK_PREDICT_FU;                                // ... on a uniformly spaced shared grid
+  constexpr bool PRED_LIKE = TASK == TASK_PREDICT || TASK == TASK_FACTOR || PF;
   double* vz = PRED_LIKE ? noise : vr + LD;
   double* va = PRED_LIKE ? vr : vz + LD;
   double* vd = va + LD;
   double* v1 = vd + LD;
   double* vu = v1 + LD;
 
-  const int split = (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) ? a.split : 1;
+  const int split = (TASK == TASK_PREDICT || PF) ? a.split : 1;
   const int64_t n_work = (a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj) * split;
   // factor workspace of one object: NT tiles in fragment order followed by alpha (LD doubles)
   constexpr int WS = NT * TILE + LD;
   __shared__ __align__(8) unsigned long long s_mbar;       // TMA completion barrier (TASK_PREDICT_F)
   unsigned mbar_parity = 0;
-  if (TASK == TASK_PREDICT_F) {
+  if (PF) {
     if (lane == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(&s_mbar)));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,11 +175,23 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       const bool in = i < nx.n;
       if (DIM == 1) { nx.x[k] = in ? a.x[nx.o0 + i] : 0.0; nx.y2[k] = 0.0; }
       else { nx.x[k] = in ? a.x[2 * (nx.o0 + i)] : 0.0; nx.y2[k] = in ? a.x[2 * (nx.o0 + i) + 1] : 0.0; }
-      if (TASK == TASK_PREDICT_F) { nx.ye[k] = 0.0; nx.r[k] = 0.0; continue; }
+      if (PF) { nx.ye[k] = 0.0; nx.r[k] = 0.0; continue; }
       nx.ye[k] = (in && a.yerr) ? a.yerr[nx.o0 + i] : 0.0;
       nx.r[k] = in ? (a.y[nx.o0 + i] - (a.y0 ? a.y0[nx.o0 + i] : 0.0)) : 0.0;
     }
   };
+  // Uniform shared grid (UNI): g_j = g_first + j*delta.  Within a pass of 16 grid rows anchored at row j0,
+  //   exp(h00 (g_j0 + k delta - x)^2) = E_a(x) * R(x)^k * C_k,  E_a = exp(h00 u^2), R = exp(2 h00 delta u), u = g_j0 - x,
+  // C_k = exp(h00 k^2 delta^2): two exps per object point and pass instead of one per (grid row, object point).
+  // The caller guarantees l >= |delta|: whenever E_a underflows every product it scales is < 1e-110.
+  double uni_g0 = 0.0, uni_delta = 0.0, uni_c0 = 1.0, uni_c1 = 1.0, uni_2hd = 0.0;
+  if (UNI) {
+    uni_g0 = a.xnew[0];
+    uni_delta = (a.xnew[a.m_shared - 1] - uni_g0) / (double)(a.m_shared - 1);
+    const double k0 = (double)L.g * uni_delta, k1 = (double)(L.g + 8) * uni_delta;
+    uni_c0 = cgp_exp(cov.h00 * k0 * k0); uni_c1 = cgp_exp(cov.h00 * k1 * k1);
+    uni_2hd = 2.0 * cov.h00 * uni_delta;
+  }
   int64_t w = blockIdx.x, w_nxt = (int64_t)blockIdx.x + gridDim.x, t_next = 0;
   Next nx;
   fetch(w, nx);
@@ -206,12 +220,15 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         vr[i] = nx.r[k]; rsum += nx.r[k];
       }
     }
+    double xo[NR];                                       // UNI: this lane owns columns lane, lane+32
+#pragma unroll
+    for (int k = 0; k < NR; ++k) xo[k] = UNI ? nx.x[k] : 0.0;
     fetch(w_nxt, nx);
     __syncwarp();
     if (TASK == TASK_LOO) rsum = red_g(red_t(rsum));
     double lp_m = 1.0; int lp_e = 0; int bad = 0;
     const bool want_u = (TASK == TASK_LOO) && (a.loo_mode == 1);
-    if (TASK == TASK_PREDICT_F) {
+    if (PF) {
       // L^-1 tiles + alpha of this object: one TMA bulk copy global -> shared, completion on an mbarrier
       const unsigned mb = (unsigned)__cvta_generic_to_shared(&s_mbar);
       if (lane == 0) {
@@ -232,7 +249,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       }
       mbar_parity ^= 1;
     }
-    if (TASK != TASK_PREDICT_F) {
+    if (!PF) {
 
     // ---------------- phase K: covariance tiles, parked in their slots (accumulator values at
     // fragment-order positions).  Two tiles per pass, unrolled twice: 8 exp chains per lane.
@@ -429,7 +446,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     }
     __syncwarp();
     if (lane == 0 && part == 0) a.info[b] = bad;
-    }   // TASK != TASK_PREDICT_F
+    }   // !PF
 
     if (TASK == TASK_FACTOR) {
       if (a.ll) {                                        // the likelihood comes for free: z and the pivots are here
@@ -481,7 +498,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       continue;
     }
 
-    if (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) {
+    if (TASK == TASK_PREDICT || PF) {
       // ---------------- two blocks of 8 grid points per pass
       const int64_t g0 = a.goff ? a.goff[b] : 0;
       const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
@@ -495,7 +512,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           const int64_t m = 8 * (rb + u) + L.g;
           const bool lv = m < m_pts;
           pgx[u] = 0.0; pgy[u] = 0.0;
-          if (lv) {
+          if (lv && !UNI) {
             if (DIM == 1) pgx[u] = a.xnew[g0 + m];
             else { pgx[u] = a.xnew[2 * (g0 + m)]; pgy[u] = a.xnew[2 * (g0 + m) + 1]; }
           }
@@ -515,6 +532,42 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         // cross-covariance fragments (no amplitude): 4 NB independent exps per lane
         double h0[2][NB], h1[2][NB];
         double pm[2] = {0.0, 0.0}, pm2[2] = {0.0, 0.0};
+        if constexpr (UNI) {
+          double2* anch = reinterpret_cast<double2*>(px);      // {E_a, R} per object point (px + noise: 2 LD doubles)
+          __syncwarp();                                        // the previous pass has read its anchors
+          const double gj0 = fma((double)(8 * rb), uni_delta, uni_g0);
+#pragma unroll
+          for (int k = 0; k < NR; ++k) {
+            const int c = k * 32 + lane;
+            const double uu = gj0 - xo[k];
+            double ea = cgp_exp(cov.h00 * uu * uu), rr = cgp_exp(uni_2hd * uu);
+            // padding columns and underflowed anchors contribute exactly 0 (R = 0 keeps 0 * R^k away from 0 * inf);
+            // the consumers below then need no masks: rows past the end of the grid are never stored
+            ea = (c < n && ea > 0.0) ? ea : 0.0;
+            rr = (ea > 0.0) ? rr : 0.0;
+            if (c < LD) anch[c] = make_double2(ea, rr);
+          }
+          __syncwarp();
+          const bool b1 = L.g & 1, b2 = L.g & 2, b4 = L.g & 4;
+#pragma unroll
+          for (int P = 0; P < NB; ++P) {
+            const int c0 = 8 * P + L.t, c1 = c0 + 4;
+            const double2 A0 = anch[c0], A1 = anch[c1];
+            const double al0 = va[c0], al1 = va[c1];
+            // R^g by squaring (g is fixed per lane: predicated multiplies), R^(g+8) = R^g R^8
+            const double r02 = A0.y * A0.y, r04 = r02 * r02, r08 = r04 * r04;
+            const double r12 = A1.y * A1.y, r14 = r12 * r12, r18 = r14 * r14;
+            double p0 = b1 ? A0.y : 1.0, p1 = b1 ? A1.y : 1.0;
+            if (b2) { p0 *= r02; p1 *= r12; }
+            if (b4) { p0 *= r04; p1 *= r14; }
+            const double t0 = A0.x * p0, t1 = A1.x * p1;
+            const double e00 = t0 * uni_c0, e01 = (t0 * r08) * uni_c1;
+            const double e10 = t1 * uni_c0, e11 = (t1 * r18) * uni_c1;
+            h0[0][P] = e00; h0[1][P] = e01; h1[0][P] = e10; h1[1][P] = e11;
+            pm[0] = fma(e00, al0, pm[0]); pm[1] = fma(e01, al0, pm[1]);
+            pm2[0] = fma(e10, al1, pm2[0]); pm2[1] = fma(e11, al1, pm2[1]);
+          }
+        } else {
 #pragma unroll
         for (int P = 0; P < NB; ++P) {
           const int c0 = 8 * P + L.t, c1 = c0 + 4;
@@ -530,6 +583,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
             h0[u][P] = e0; h1[u][P] = e1;
             pm[u] = fma(e0, al0, pm[u]); pm2[u] = fma(e1, al1, pm2[u]);
           }
+        }
         }
         double acc0[2][NB], acc1[2][NB];
 #pragma unroll
@@ -783,7 +837,7 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
   }
-  const int64_t n_work = a.n_obj * ((TASK == TASK_PREDICT || TASK == TASK_PREDICT_F) ? a.split : 1);
+  const int64_t n_work = a.n_obj * ((TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU) ? a.split : 1);
   static int cap = -1;                                    // experiment knob: CGP_GP64_PER_SM=<blocks per SM>
   if (cap < 0) { const char* e = getenv("CGP_GP64_PER_SM"); cap = e ? atoi(e) : 0; }
   int64_t grid = (int64_t)sm_count * ((cap > 0 && cap < per_sm) ? cap : per_sm);
@@ -816,7 +870,7 @@ int launch64_nb(int nb, const SmallArgs& a, cudaStream_t stream) {
 // One (DIM, TASK) pair per translation unit (build.py compiles this file six times with
 // -DCGP64_DIM / -DCGP64_TASK) so the 48 static instantiations build in parallel.
 #ifndef CGP64_DIM
-#error "compile with -DCGP64_DIM=1|2 -DCGP64_TASK=0|1|2"
+#error "compile with -DCGP64_DIM=1|2 -DCGP64_TASK=0|1|2|4|5|6"
 #endif
 #define CGP64_CAT2(a, b, c, d) a##b##c##d
 #define CGP64_CAT(a, b, c, d) CGP64_CAT2(a, b, c, d)

@@ -161,7 +161,11 @@ int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
   DeviceGuard guard(s->dev);
   const size_t n = (size_t)s->n_pts, m = (size_t)s->m_grid, dim = (size_t)s->dim;
   const bool tmpl = (flags & CGP_MEAN_TEMPLATE) && new_y0;
-  const unsigned kflags = flags & ~CGP_MEAN_TEMPLATE;
+  const unsigned kflags = flags & ~(CGP_MEAN_TEMPLATE | CGP_GRID_UNIFORM);
+  // uniformly spaced grid: verified here on the host copy, once per run (the hint costs nothing when it fails)
+  const int uniform = (flags & CGP_GRID_UNIFORM) && s->dim == 1 && s->two_kernel && s->m_grid >= 2 &&
+                      cgp::uniform_grid_ok(xnew, s->m_grid, hyp);
+  const unsigned pflags = flags & ~CGP_GRID_UNIFORM;
   int64_t up = 0, down = 0;
   int rc = 0, bad = 0;
   cudaError_t e = cudaSuccess;
@@ -225,10 +229,10 @@ int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
         rc = cgp_factor_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, kflags,
                                     k.ws, k.ll, k.info, cs);
         if (rc < 0) break;
-        rc = cgp_predict_factored_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, hyp, nugget, flags, k.ws, k.info,
-                                      s->grid, nullptr, (int64_t)m, dny0, k.mean, dvar, cs);
+        rc = cgp::predict_factored((int64_t)nb, s->off, s->n_pts, s->dim, k.x, hyp, nugget, pflags, k.ws, k.info,
+                                   s->grid, nullptr, (int64_t)m, dny0, k.mean, dvar, uniform, cs);
       } else {
-        rc = cgp_predict_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, flags,
+        rc = cgp_predict_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, pflags,
                                      s->grid, nullptr, (int64_t)m, dny0, k.mean, dvar, k.info, cs);
       }
       if (rc < 0) break;

@@ -37,6 +37,11 @@
  *     `diff`): mean function of object b at grid point j = new_y0[j] +
  *     new_y0[m_shared + b] -- what mean.py:92-101 evaluates per object, without
  *     materialising (or uploading) n_obj x m_shared doubles.
+ *     CGP_GRID_UNIFORM (prediction entry points, dim 1, shared grid, shared hyp): a hint that
+ *     xnew[j] = xnew[0] + j*delta.  The library verifies it (to 4 ulp) and that l >= |delta|; the
+ *     cross-covariance of 16 grid rows is then built from two exps per data point
+ *     (exp(-(g_0 + k delta - x)^2 / 2 l^2) = E(x) R(x)^k C_k) instead of one per (grid point, data point).
+ *     Results agree with the general path to ~1e-14 relative; without the flag nothing changes.
  *   - all arithmetic is IEEE float64.
  */
 #ifndef COSMOGP_B200_H
@@ -50,6 +55,7 @@ extern "C" {
 
 #define CGP_AMP_ON_AUTOCOV 1u      /* opt-in fix of the 2D sigma^2 omission */
 #define CGP_MEAN_TEMPLATE  2u      /* new_y0 = [template on the shared grid | per-object offsets] */
+#define CGP_GRID_UNIFORM   4u      /* hint: the shared 1D grid is uniformly spaced (verified by the library) */
 
 #define CGP_SMALL_MAX_N 224        /* largest object the shared-memory path takes */
 

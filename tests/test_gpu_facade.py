@@ -179,7 +179,9 @@ def test_streamed_evaluator_matches_resident_batch(cg):
     t2, ll2, _ = batch.log_likelihood([0.5, 2.0], 0.03)
     m2, v2, _ = batch.predict([0.5, 2.0], 0.03, grid, new_y0=ny0)
     assert not info.any() and tot == t2
-    assert np.array_equal(ll, ll2) and np.array_equal(mean, m2) and np.array_equal(var, v2)
+    assert np.array_equal(ll, ll2)
+    # (batch.predict hints a uniform grid and, at >= 2048 objects, runs the recurrence kernel; the small chunks here do not)
+    assert_close(mean, m2, 1e-10, 1e-11); assert_close(var, v2, 1e-10, 1e-11)
     assert ev.h2d_bytes == (b * (4 * n + m) + m) * 8 and ev.d2h_bytes == b * (8 + 16 * m + 4)     # + the grid itself
     # shared mean (template + offset per object): same results from M + B mean values instead of B x M
     tmpl, diff = np.cos(grid / 5.0), rng.standard_normal(b)
@@ -188,7 +190,8 @@ def test_streamed_evaluator_matches_resident_batch(cg):
         ev2.host(k)[...] = v
     tot3, ll3, mean3, var3, info3 = ev2.run([0.5, 2.0], 0.03, grid)
     m4, v4, _ = batch.predict([0.5, 2.0], 0.03, grid, new_y0=tmpl[None, :] + diff[:, None])
-    assert tot3 == t2 and np.array_equal(mean3, m4) and np.array_equal(var3, v4)
+    assert tot3 == t2
+    assert_close(mean3, m4, 1e-10, 1e-11); assert_close(var3, v4, 1e-10, 1e-11)
     assert ev2.h2d_bytes == (b * (4 * n + 1) + 3 * m + m) * 8                # template once per stream, grid once
     # large chunks: ramped schedule (2048, 3276, ... up to the buffer capacity, then down again), two-kernel route
     b, n, m = 40001, 20, 16
