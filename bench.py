@@ -327,8 +327,8 @@ def main():
         "gpu_launches": int(launches),
         "fused_step": {"ms_per_step": fused_ms, "objects_per_s_per_gpu": B / (fused_ms * 1e-3),
                        "what": "LL + predict from one factorisation per object (factor kernel emits LL), resident"},
-        "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,PREDICT_F,8>: predictive mean+variance on the grid from the "
-                     "TMA-staged factor (FP64 tensor pipe, DMMA.8x8x4)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,PREDICT_FU,8>: predictive mean+variance on the (uniform) grid "
+                     "from the TMA-staged factor (FP64 tensor pipe, DMMA.8x8x4)", "achieved": achieved,
                      "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": traffic,
                      "peak_source": "FP64 DMMA m8n8k4 ceiling measured in this run (cgp_fp64_peak); MEASURED_PEAKS.json "
                                     "has no FP64 entry; DFMA ceiling %.2f" % peak_dfma,

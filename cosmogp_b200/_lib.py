@@ -42,6 +42,8 @@ SIGNATURES = {
     "cgp_streamer_destroy": (None, [_ptr]),
     "cgp_streamer_run": (_int, [_ptr, _i64] + [_ptr] * 4 + [_ptr, _dbl, _dbl, _u32] + [_ptr, _ptr] + [_ptr] * 4
                          + [C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64)]),
+    "cgp_grid_is_uniform": (_int, [_ptr, _i64, _ptr]),
+    "cgp_streamer_schedule": (_i64, [_i64, _i64, _int, _ptr, _i64]),
     "cgp_moments_dev": (_int, [_ptr, _i64, _dbl, _ptr, _ptr]),
     "cgp_fit_objects_dev": (_int, _BATCH_DEV + [_ptr] * 4 + [_ptr, _int, _dbl, _dbl, _u32, _dbl, _dbl, _int, _int] + [_ptr] * 5),
     "cgp_predict_objhyp_dev": (_int, _BATCH_DEV + [_ptr] * 4 + [_ptr, _ptr, _dbl, _dbl, _u32] + [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),

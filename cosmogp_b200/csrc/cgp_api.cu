@@ -599,6 +599,10 @@ int cgp_trsm_rows_dev(const double* a, int64_t n_pad, int64_t ld, double* v, int
   return e ? cuda_fail(e, "cgp_trsm_rows_dev") : 0;
 }
 
+int cgp_grid_is_uniform(const double* grid_host, int64_t m, const double* hyp) {
+  return uniform_grid_ok(grid_host, m, hyp);
+}
+
 int cgp_moments_dev(const double* v, int64_t n, double center, double* out2, void* stream) {
   if (n < 0 || (n && !v) || !out2) return fail(CGP_ERR_ARG, "cgp_moments_dev: NULL argument");
   int e = large_moments(v, n, center, out2, (cudaStream_t)stream);

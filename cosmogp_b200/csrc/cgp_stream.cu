@@ -106,6 +106,13 @@ void release(cgp_streamer* s) {
 
 extern "C" {
 
+int64_t cgp_streamer_schedule(int64_t n_obj, int64_t chunk_objects, int n_pts, int64_t* sizes, int64_t max_sizes) {
+  if (n_obj < 0 || chunk_objects <= 0 || n_pts <= 0) return -1;
+  const std::vector<int64_t> sz = chunk_schedule(n_obj, chunk_objects, n_pts <= 64 && chunk_objects >= 2048);
+  for (size_t i = 0; i < sz.size() && (int64_t)i < max_sizes && sizes; ++i) sizes[i] = sz[i];
+  return (int64_t)sz.size();
+}
+
 int cgp_streamer_create(int64_t chunk_objects, int n_pts, int64_t m_grid, int dim, int n_streams, cgp_streamer** out) {
   if (!out) return sfail(-1, "cgp_streamer_create: out is NULL");
   *out = nullptr;

@@ -98,6 +98,10 @@ int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
  *      ll_sum = ll[0] + ll[1] + ... in that order.  Returns the number of objects whose covariance was not
  *      positive definite (their info[] != 0), or < 0.  h2d_bytes / d2h_bytes (may be NULL) count the copies. */
 typedef struct cgp_streamer cgp_streamer;
+/* host only: the chunk sizes cgp_streamer_run uses for n_obj objects (a ramp 2048, x1.6 ... up to chunk_objects,
+ * equal chunks in the middle, a x2 ramp down; plain equal chunks when chunk_objects < 2048 or n_pts > 64).
+ * Writes up to max_sizes entries, returns the number of chunks (sizes may be NULL), or -1. */
+int64_t cgp_streamer_schedule(int64_t n_obj, int64_t chunk_objects, int n_pts, int64_t* sizes, int64_t max_sizes);
 int cgp_streamer_create(int64_t chunk_objects, int n_pts, int64_t m_grid, int dim, int n_streams, cgp_streamer** out);
 void cgp_streamer_destroy(cgp_streamer* s);
 int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
@@ -244,6 +248,11 @@ int cgp_large_predict_dev(const double* a, int64_t n, int64_t n_pad, int64_t ld,
 
 /* v_m = L^-1 h_m for `rows` rows of V (rows x n_pad, rows % 128 == 0), in place. */
 int cgp_trsm_rows_dev(const double* a, int64_t n_pad, int64_t ld, double* v, int64_t ldv, int64_t rows, void* stream);
+
+/* host only: 1 when a shared 1D grid (host array of m points) qualifies for the CGP_GRID_UNIFORM kernel with
+ * hyperparameters hyp = [sigma, l]: grid[j] = grid[0] + j*delta to within 4 ulp and |l| >= |delta| > 0.
+ * This is the check the prediction entry points apply to the hint. */
+int cgp_grid_is_uniform(const double* grid_host, int64_t m, const double* hyp);
 
 /* Centred moments of a device vector: out2[0] = sum (v[i] - center), out2[1] = sum (v[i] - center)^2
  * (out2: 2 doubles on the device; fixed summation order, reproducible).  Two calls give what

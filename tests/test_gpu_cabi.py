@@ -441,6 +441,10 @@ def test_uniform_grid_fast_path(L):
         mo, vo = O.predict(y[i], x[i], [0.6, 2.5], 0.04, grid, ye[i], full_cov=False)
         (m2, v2), (m3, v3) = both(x, y, ye, [0.6, 2.5], 0.04, grid)
         assert_close(m3[i], mo, RTOL, 1e-12); assert_close(v3[i], vo, RTOL, 1e-13)
+    # a descending grid is uniform too (negative spacing)
+    x = np.sort(rng.uniform(-10, 40, (2200, 30)), axis=1); y = rng.standard_normal((2200, 30)); ye = np.full((2200, 30), 0.2)
+    (m0, v0), (m1, v1) = both(x, y, ye, [0.6, 2.5], 0.04, np.linspace(42, -12, 90))
+    assert_close(m1, m0, 1e-10, 1e-11); assert_close(v1, v0, 1e-10, 1e-11); assert not np.array_equal(m1, m0)
     # data far from the grid and a short length scale: anchors underflow, true values are negligible
     b, n, m = 2500, 30, 100
     x = np.sort(rng.uniform(-400, 400, (b, n)), axis=1); y = rng.standard_normal((b, n)); ye = np.full((b, n), 0.2)

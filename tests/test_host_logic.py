@@ -1,0 +1,53 @@
+"""CPU-only checks of the host-side logic inside the library (no device calls)."""
+import ctypes as C
+
+import numpy as np
+
+
+def _lib():
+    from cosmogp_b200 import build, _lib
+    build.build()
+    return _lib
+
+
+def test_uniform_grid_check():
+    """The check applied to the CGP_GRID_UNIFORM hint: spacing uniform to a few ulp, l >= spacing > 0."""
+    L = _lib()
+    ok = lambda g, l: L.lib().cgp_grid_is_uniform(L.hptr(np.ascontiguousarray(g, dtype=np.float64)), len(g),
+                                                 L.hptr(np.array([0.5, l])))
+    g = np.linspace(-10, 40, 100)
+    assert ok(g, 2.0) == 1 and ok(g, -2.0) == 1                  # the sign of l is irrelevant (kernel.py:71 squares it)
+    assert ok(g[::-1].copy(), 2.0) == 1                          # descending grids are uniform too
+    assert ok(g, 0.5) == 0                                       # l < spacing (0.505): anchors could underflow
+    assert ok(g, float("nan")) == 0
+    assert ok(np.arange(100) * 0.1 + 3.0, 1.0) == 1              # arange-style grids
+    bent = g.copy(); bent[50] += 1e-12
+    assert ok(bent, 2.0) == 0
+    assert ok(np.sort(np.random.default_rng(0).uniform(0, 1, 50)), 2.0) == 0
+    assert ok(np.array([1.0]), 2.0) == 0 and ok(np.array([1.0, 1.0]), 2.0) == 0      # fewer than two points, zero spacing
+    assert ok(np.array([0.0, 1.0]), 2.0) == 1
+    assert ok(np.array([0.0, np.inf]), 2.0) == 0
+
+
+def test_streamer_chunk_schedule():
+    """Chunk sizes of cgp_streamer_run: they cover the batch exactly, never exceed the buffers, ramp up and down."""
+    L = _lib()
+
+    def sched(n_obj, cap, n_pts=60):
+        buf = np.zeros(4096, dtype=np.int64)
+        k = L.lib().cgp_streamer_schedule(n_obj, cap, n_pts, L.hptr(buf), len(buf))
+        assert 0 <= k <= len(buf)
+        return buf[:k]
+
+    for n_obj, cap in ((100000, 16667), (100000, 25000), (100000, 2500), (40001, 10001), (5003, 715), (1, 4096),
+                       (0, 4096), (9000, 4096), (2049, 2048), (1000000, 50000)):
+        s = sched(n_obj, cap)
+        assert s.sum() == n_obj and (s > 0).all() and (len(s) == 0 or s.max() <= cap), (n_obj, cap, s)
+    s = sched(100000, 16667)
+    assert s[0] == 2048 and s[-1] == 2048 and list(s[:4]) == [2048, 3276, 5241, 8385]        # x1.6 up
+    assert list(s[-3:]) == [8192, 4096, 2048]                                                  # x2 down
+    assert (np.diff(s[:5]) > 0).all()
+    assert len(set(sched(100000, 2500))) == 1                       # small buffers: equal chunks
+    assert len(set(sched(100000, 16667, n_pts=100))) <= 2           # objects beyond the one-warp kernels: equal chunks
+    assert L.lib().cgp_streamer_schedule(10, 0, 60, None, 0) == -1
+    assert L.lib().cgp_streamer_schedule(100000, 16667, 60, None, 0) == len(s)
