@@ -867,8 +867,8 @@ int launch64_nb(int nb, const SmallArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-// One (DIM, TASK) pair per translation unit (build.py compiles this file six times with
-// -DCGP64_DIM / -DCGP64_TASK) so the 48 static instantiations build in parallel.
+// One (DIM, TASK) pair per translation unit (build.py compiles this file eleven times with
+// -DCGP64_DIM / -DCGP64_TASK) so the 88 static instantiations build in parallel.
 #ifndef CGP64_DIM
 #error "compile with -DCGP64_DIM=1|2 -DCGP64_TASK=0|1|2|4|5|6"
 #endif
