@@ -274,11 +274,14 @@ def main():
     # ---- end to end through the numpy-in/numpy-out layer: every step uploads the step's inputs from
     # pinned host memory, runs LL + predict and downloads ll/mean/var; chunks of objects (ramping up from
     # 2048 to a quarter of the batch and down again) are pipelined: one upload stream, one download stream,
-    # kernels of consecutive chunks on 6 compute streams -- one native call per step (cgp_streamer_run)
+    # kernels of consecutive chunks on 8 compute streams -- one native call per step (cgp_streamer_run)
     from cosmogp_b200.batch import StreamedEvaluator
-    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "6")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "6")), shared_mean=True)
-    for name, arr in (("x", x), ("y", y), ("y0", y0.reshape(B, N_EPOCH)), ("y_err", ye), ("template", tmpl), ("diff", d)):
+    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "8")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "8")), shared_mean=True)
+    for name, arr in (("x", x), ("y", y), ("y_err", ye), ("template", tmpl), ("diff", d)):
         ev_e2e.host(name)[...] = arr
+    # the mean at the epochs (template spline + offset, cosmogp/mean.py:84-90) is evaluated on the device from the
+    # template itself -- the reference's own inputs (Mean_Y, Time_mean, diff) -- instead of uploading y0
+    ev_e2e.set_mean_template(tmean, ymean)
 
     def e2e_step():
         tot, ll_h, mean, var, info = ev_e2e.run(HYP, NUGGET, grid)

@@ -40,8 +40,10 @@ SIGNATURES = {
     "cgp_ll_objhyp_dev": (_int, _BATCH_DEV + [_ptr] * 4 + [_ptr, _ptr, _dbl, _dbl, _u32, _ptr, _i64, _ptr, _ptr, _ptr]),
     "cgp_streamer_create": (_int, [_i64, _int, _i64, _int, _int, C.POINTER(_ptr)]),
     "cgp_streamer_destroy": (None, [_ptr]),
+    "cgp_streamer_set_mean_spline": (_int, [_ptr, _ptr, _ptr, _int]),
     "cgp_streamer_run": (_int, [_ptr, _i64] + [_ptr] * 4 + [_ptr, _dbl, _dbl, _u32] + [_ptr, _ptr] + [_ptr] * 4
                          + [C.POINTER(_dbl), C.POINTER(_i64), C.POINTER(_i64)]),
+    "cgp_spline_mean_dev": (_int, [_ptr, _ptr, _int, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr]),
     "cgp_grid_is_uniform": (_int, [_ptr, _i64, _ptr]),
     "cgp_streamer_schedule": (_i64, [_i64, _i64, _int, _ptr, _i64]),
     "cgp_moments_dev": (_int, [_ptr, _i64, _dbl, _ptr, _ptr]),

@@ -420,6 +420,21 @@ class StreamedEvaluator:
         """numpy view of a pinned staging array: fill inputs / read outputs in place."""
         return self.h[name].numpy()
 
+    def set_mean_template(self, time_mean, mean_y):
+        """The shared mean as the reference defines it (mean.py:28-31: cubic spline through (Time_mean, Mean_Y)):
+        with shared_mean=True, y0 = spline(x) + diff[sn] is then evaluated on the device like FITPACK would
+        (cgp_spline_mean_dev) instead of being uploaded ("y0" is ignored), and "template" is filled with the
+        spline on `grid` at the next run()."""
+        import scipy.interpolate as inter
+        assert self.shared_mean and self.dim == 1, "a 1D template needs shared_mean=True"
+        self._spline = inter.InterpolatedUnivariateSpline(time_mean, mean_y)
+        t, c, k = self._spline._eval_args
+        assert k == 3
+        t = np.ascontiguousarray(t, dtype=np.float64); c = np.ascontiguousarray(c, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cgp_streamer_set_mean_spline(self._handle, _lib.hptr(t), _lib.hptr(c), len(t)),
+                       "cgp_streamer_set_mean_spline")
+
     def run(self, hyp, nugget, grid, floor=0.0, flags=0):
         """-> (ll_sum, ll (B,), mean (B,M), var (B,M), info (B,)) as numpy views of the pinned outputs."""
         C = _lib.C
@@ -428,8 +443,12 @@ class StreamedEvaluator:
         assert g.shape[0] == self.M, "grid must have the %d points the evaluator was built for" % self.M
         p = lambda t: t.data_ptr()
         mean_fn = self._packed_mean if self.shared_mean else self.h["new_y0"]
+        spline = getattr(self, "_spline", None)
+        if spline is not None:
+            self.h["template"].numpy()[...] = spline(g)
         total, up, down = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
-        rc = _lib.lib().cgp_streamer_run(self._handle, self.B, p(self.h["x"]), p(self.h["y"]), p(self.h["y0"]), p(self.h["y_err"]),
+        rc = _lib.lib().cgp_streamer_run(self._handle, self.B, p(self.h["x"]), p(self.h["y"]),
+                                         None if spline is not None else p(self.h["y0"]), p(self.h["y_err"]),
                                          _lib.hptr(h), float(nugget), float(floor),
                                          int(flags) | (_lib.CGP_MEAN_TEMPLATE if self.shared_mean else 0) | _lib.CGP_GRID_UNIFORM,
                                          _lib.hptr(g), p(mean_fn), p(self.h["ll"]), p(self.h["mean"]), p(self.h["var"]),

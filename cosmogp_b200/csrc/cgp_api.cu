@@ -599,6 +599,15 @@ int cgp_trsm_rows_dev(const double* a, int64_t n_pad, int64_t ld, double* v, int
   return e ? cuda_fail(e, "cgp_trsm_rows_dev") : 0;
 }
 
+int cgp_spline_mean_dev(const double* t, const double* c, int n_knots, const double* x, int64_t n_pts,
+                        const int64_t* off, int64_t n_obj, const double* diff, double* out, void* stream) {
+  if (n_pts < 0 || (n_pts && (!t || !c || !x || !out))) return fail(CGP_ERR_ARG, "cgp_spline_mean_dev: NULL argument");
+  if (n_knots < 8) return fail(CGP_ERR_ARG, "cgp_spline_mean_dev: a cubic spline has at least 8 knots, got %d", n_knots);
+  if (diff && (!off || n_obj <= 0)) return fail(CGP_ERR_ARG, "cgp_spline_mean_dev: diff needs the CSR offsets");
+  int e = large_spline_mean(t, c, n_knots, x, n_pts, off, n_obj, diff, out, (cudaStream_t)stream);
+  return e ? cuda_fail(e, "cgp_spline_mean_dev") : 0;
+}
+
 int cgp_grid_is_uniform(const double* grid_host, int64_t m, const double* hyp) {
   return uniform_grid_ok(grid_host, m, hyp);
 }

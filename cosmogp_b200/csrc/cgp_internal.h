@@ -108,6 +108,8 @@ int large_trsm_rows(const double* a, int64_t n_pad, int64_t ld, double* v, int64
 int large_stream_mean(int dim, const Cov& cov, const double* x, const double* alpha, int64_t n,
                       const double* xnew, const double* new_y0, int64_t m, double* mean, cudaStream_t st);
 int large_row_var(const double* v, int64_t ldv, int64_t n_pad, int64_t rows, double amp_star, double* var, cudaStream_t st);
+int large_spline_mean(const double* t, const double* c, int nt, const double* x, int64_t n_pts, const int64_t* off,
+                      int64_t n_obj, const double* diff, double* out, cudaStream_t st);
 int large_moments(const double* v, int64_t n, double center, double* out2, cudaStream_t st);
 int large_dot_sq(const double* v, int64_t n, double* out, cudaStream_t st);
 int large_residual(const double* y, const double* y0, int64_t n, int64_t n_pad, double* r, cudaStream_t st);

@@ -315,6 +315,56 @@ __global__ void sum_kernel(const double* v, int64_t n, double* out) {         //
     if (threadIdx.x == 0) out[0] = acc;
   }
 }
+// Mean function at the epochs on the device: the cubic B-spline scipy's InterpolatedUnivariateSpline holds
+// (knots t[0..nt), coefficients c) evaluated as FITPACK does (splev.f: knot interval by search, clamped to the end
+// intervals = polynomial extrapolation; fpbspl.f: de Boor recurrence; same operation order, no FMA contraction),
+// plus the object's offset diff[b] (cosmogp/mean.py:28-31,84-90).  One thread per point; the object of a point
+// comes from a binary search in the CSR offsets.
+__global__ void __launch_bounds__(256) spline_mean_kernel(const double* __restrict__ t, const double* __restrict__ c, int nt,
+                                                          const double* __restrict__ x, int64_t n_pts,
+                                                          const int64_t* __restrict__ off, int64_t n_obj,
+                                                          const double* __restrict__ diff, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const double arg = x[i];
+  constexpr int K = 3, K1 = K + 1;
+  const int nk1 = nt - K1;                       // 1-based: l in [K1, nk1] with t(l) <= arg < t(l+1) where possible
+  int lo = K1, hi = nk1;                         // largest l in [lo, hi] with t(l) <= arg (lo when none)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (t[mid - 1] <= arg) lo = mid; else hi = mid - 1;
+  }
+  const int l = lo;
+  double h[K1 + 1], hh[K1];
+  h[0] = 1.0;
+#pragma unroll
+  for (int j = 1; j <= K; ++j) {
+#pragma unroll
+    for (int q = 0; q < j; ++q) hh[q] = h[q];
+    h[0] = 0.0;
+#pragma unroll
+    for (int q = 1; q <= j; ++q) {
+      const double tli = t[l + q - 1], tlj = t[l + q - j - 1];
+      if (tli == tlj) { h[q] = 0.0; continue; }
+      const double f = __ddiv_rn(hh[q - 1], __dsub_rn(tli, tlj));
+      h[q - 1] = __dadd_rn(h[q - 1], __dmul_rn(f, __dsub_rn(tli, arg)));
+      h[q] = __dmul_rn(f, __dsub_rn(arg, tlj));
+    }
+  }
+  double sp = 0.0;
+#pragma unroll
+  for (int j = 0; j < K1; ++j) sp = __dadd_rn(sp, __dmul_rn(c[l - K1 + j], h[j]));
+  if (diff) {
+    int64_t a = 0, b = n_obj - 1;                // object of point i: last b with off[b] <= i
+    while (a < b) {
+      const int64_t mid = (a + b + 1) >> 1;
+      if (off[mid] <= i) a = mid; else b = mid - 1;
+    }
+    sp = __dadd_rn(sp, diff[a]);
+  }
+  out[i] = sp;
+}
+
 // Centred moments of a long vector, for scipy.stats.norm.fit of the pulls (cosmogp/pull.py:102) without a
 // download: partial[2*blk] = sum (v - c), partial[2*blk+1] = sum (v - c)^2 over the block's contiguous
 // segment (16-byte loads, HBM bound); a second one-CTA pass adds the partials in a fixed order.
@@ -610,6 +660,13 @@ int large_row_var(const double* v, int64_t ldv, int64_t n_pad, int64_t rows, dou
 }
 int large_dot_sq(const double* v, int64_t n, double* out, cudaStream_t st) {
   dot_sq_kernel<<<1, 1024, 0, st>>>(v, n, out); count_launch(); return (int)cudaGetLastError();
+}
+int large_spline_mean(const double* t, const double* c, int nt, const double* x, int64_t n_pts, const int64_t* off,
+                      int64_t n_obj, const double* diff, double* out, cudaStream_t st) {
+  if (n_pts <= 0) return 0;
+  spline_mean_kernel<<<(unsigned)((n_pts + 255) / 256), 256, 0, st>>>(t, c, nt, x, n_pts, off, n_obj, diff, out);
+  count_launch();
+  return (int)cudaGetLastError();
 }
 int large_moments(const double* v, int64_t n, double center, double* out2, cudaStream_t st) {
   const int nblk = n < (int64_t)1 << 16 ? 1 : 148 * 8;

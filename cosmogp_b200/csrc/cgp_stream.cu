@@ -35,6 +35,7 @@ struct cgp_streamer {
   // all uploads go through ONE stream and all downloads through another, in chunk order: copies issued from
   // several streams share the link, so the first (small) chunk would arrive no sooner than the ones behind it
   cudaStream_t up = nullptr, dn = nullptr;
+  double* spl_t = nullptr; double* spl_c = nullptr; int spl_n = 0;     // mean template as a cubic B-spline (optional)
 };
 
 namespace {
@@ -99,6 +100,8 @@ void release(cgp_streamer* s) {
   if (s->dn) cudaStreamDestroy(s->dn);
   if (s->off) cudaFree(s->off);
   if (s->grid) cudaFree(s->grid);
+  if (s->spl_t) cudaFree(s->spl_t);
+  if (s->spl_c) cudaFree(s->spl_c);
   delete s;
 }
 
@@ -156,6 +159,23 @@ int cgp_streamer_create(int64_t chunk_objects, int n_pts, int64_t m_grid, int di
 }
 
 void cgp_streamer_destroy(cgp_streamer* s) { release(s); }
+
+int cgp_streamer_set_mean_spline(cgp_streamer* s, const double* t, const double* c, int n_knots) {
+  if (!s) return sfail(-1, "cgp_streamer_set_mean_spline: NULL streamer");
+  DeviceGuard guard(s->dev);
+  if (s->spl_t) { cudaFree(s->spl_t); s->spl_t = nullptr; }
+  if (s->spl_c) { cudaFree(s->spl_c); s->spl_c = nullptr; }
+  s->spl_n = 0;
+  if (!t || !c || n_knots == 0) return 0;                     // cleared
+  if (s->dim != 1 || n_knots < 8) return sfail(-1, "cgp_streamer_set_mean_spline: cubic spline of a 1D template (>= 8 knots) expected");
+  cudaError_t e = dalloc(&s->spl_t, (size_t)n_knots);
+  if (e == cudaSuccess) e = dalloc(&s->spl_c, (size_t)n_knots);
+  if (e == cudaSuccess) e = cudaMemcpy(s->spl_t, t, sizeof(double) * n_knots, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(s->spl_c, c, sizeof(double) * n_knots, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return sfail(-100 - (int)e, "cgp_streamer_set_mean_spline", e);
+  s->spl_n = n_knots;
+  return 0;
+}
 
 int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
                      const double* x, const double* y, const double* y0, const double* y_err,
@@ -222,6 +242,11 @@ int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
     if ((e = cudaStreamWaitEvent(cs, k.up_done, 0)) != cudaSuccess) break;
     if (reused && (e = cudaStreamWaitEvent(cs, k.dn_done, 0)) != cudaSuccess) break;   // outputs still downloading
     const double* dy0 = y0 ? k.y0 : nullptr;
+    if (!y0 && s->spl_n && tmpl) {                   // mean at the epochs = spline(x) + the object's offset, on the device
+      rc = cgp_spline_mean_dev(s->spl_t, s->spl_c, s->spl_n, k.x, (int64_t)(nb * n), s->off, (int64_t)nb, k.ny0 + m, k.y0, cs);
+      if (rc < 0) break;
+      dy0 = k.y0;
+    }
     const double* dye = y_err ? k.ye : nullptr;
     const double* dny0 = (m && new_y0) ? k.ny0 : nullptr;
     double* dvar = var ? k.var : nullptr;

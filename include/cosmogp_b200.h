@@ -104,6 +104,10 @@ typedef struct cgp_streamer cgp_streamer;
 int64_t cgp_streamer_schedule(int64_t n_obj, int64_t chunk_objects, int n_pts, int64_t* sizes, int64_t max_sizes);
 int cgp_streamer_create(int64_t chunk_objects, int n_pts, int64_t m_grid, int dim, int n_streams, cgp_streamer** out);
 void cgp_streamer_destroy(cgp_streamer* s);
+/* Optional: the mean template as scipy's cubic spline (host arrays t, c of n_knots entries, see cgp_spline_mean_dev).
+ * A run with y0 == NULL and CGP_MEAN_TEMPLATE then evaluates y0 = S(x) + offset of the object on the device instead
+ * of uploading it.  t == NULL clears it. */
+int cgp_streamer_set_mean_spline(cgp_streamer* s, const double* t, const double* c, int n_knots);
 int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
                      const double* x, const double* y, const double* y0, const double* y_err,
                      const double* hyp, double nugget, double floor, unsigned flags,
@@ -248,6 +252,14 @@ int cgp_large_predict_dev(const double* a, int64_t n, int64_t n_pad, int64_t ld,
 
 /* v_m = L^-1 h_m for `rows` rows of V (rows x n_pad, rows % 128 == 0), in place. */
 int cgp_trsm_rows_dev(const double* a, int64_t n_pad, int64_t ld, double* v, int64_t ldv, int64_t rows, void* stream);
+
+/* The mean function at the epochs, on the device: out[i] = S(x[i]) + diff[object of i], S the cubic spline through
+ * the template (cosmogp/mean.py:28-31: InterpolatedUnivariateSpline(Time_mean, Mean_Y)) given by its FITPACK knots t
+ * (n_knots) and B-spline coefficients c (n_knots; what scipy keeps in spl._eval_args), evaluated like FITPACK's splev
+ * (extrapolating with the end polynomials).  dim 1 only.  off / n_obj / diff may be NULL / 0 / NULL (no offsets).
+ * All pointers are device pointers.  Saves the upload of one double per data point (mean.py:84-90's y0). */
+int cgp_spline_mean_dev(const double* t, const double* c, int n_knots, const double* x, int64_t n_pts,
+                        const int64_t* off, int64_t n_obj, const double* diff, double* out, void* stream);
 
 /* host only: 1 when a shared 1D grid (host array of m points) qualifies for the CGP_GRID_UNIFORM kernel with
  * hyperparameters hyp = [sigma, l]: grid[j] = grid[0] + j*delta to within 4 ulp and |l| >= |delta| > 0.

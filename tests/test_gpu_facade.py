@@ -123,6 +123,50 @@ def test_build_pull_modes(cg):
     assert_close(bc._pull[len(ys) + 1], split(r["pullB"], off)[1], 1e-8, 1e-11)
 
 
+def test_mean_spline_on_device(cg):
+    """cgp_spline_mean_dev = scipy's InterpolatedUnivariateSpline (FITPACK splev) + per-object offset, including
+    extrapolation beyond the template; and the streamed evaluator computing y0 from it instead of uploading it."""
+    import torch
+    import scipy.interpolate as inter
+    from cosmogp_b200 import _lib
+    from cosmogp_b200.batch import StreamedEvaluator
+    rng = np.random.default_rng(4)
+    tm = np.sort(rng.uniform(-15, 45, 40)); ym = np.sin(tm / 5) + 0.1 * rng.standard_normal(40)
+    spl = inter.InterpolatedUnivariateSpline(tm, ym)
+    t, c, k = spl._eval_args
+    sizes = rng.integers(0, 70, 500); off = np.zeros(501, dtype=np.int64); off[1:] = np.cumsum(sizes)
+    x = np.concatenate([rng.uniform(-30, 60, off[-1] - 42), tm, [tm[0], tm[-1]]]); diff = rng.standard_normal(500)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    out = torch.empty(len(x), dtype=torch.float64, device="cuda")
+    args = [dev(t), dev(c), dev(x), dev(off), dev(diff)]
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().cgp_spline_mean_dev(args[0].data_ptr(), args[1].data_ptr(), len(t), args[2].data_ptr(), len(x),
+                                              args[3].data_ptr(), 500, args[4].data_ptr(), out.data_ptr(), st), "spline")
+    ref = spl(x) + np.repeat(diff, sizes)
+    assert np.array_equal(out.cpu().numpy(), ref)               # same operations in the same order as FITPACK
+    _lib.check(_lib.lib().cgp_spline_mean_dev(args[0].data_ptr(), args[1].data_ptr(), len(t), args[2].data_ptr(), len(x),
+                                              None, 0, None, out.data_ptr(), st), "spline")
+    assert np.array_equal(out.cpu().numpy(), spl(x))
+    # streamed evaluator: y0 evaluated on the device from the template == y0 computed by scipy and uploaded
+    b, n, m = 6000, 30, 40
+    xs = np.sort(rng.uniform(-10, 40, (b, n)), axis=1); ys = rng.standard_normal((b, n)); ye = np.full((b, n), 0.2)
+    d = rng.standard_normal(b); grid = np.linspace(-10, 40, m)
+    res = []
+    for on_device in (False, True):
+        ev = StreamedEvaluator(b, n, m, n_chunks=2, n_streams=2, shared_mean=True)
+        for kk, v in (("x", xs), ("y", ys), ("y_err", ye), ("diff", d), ("template", spl(grid))):
+            ev.host(kk)[...] = v
+        if on_device:
+            ev.set_mean_template(tm, ym)
+            ev.host("y0")[...] = np.nan                          # must not be read
+        else:
+            ev.host("y0")[...] = spl(xs.ravel()).reshape(b, n) + d[:, None]
+        tot, ll, mean, var, info = ev.run([0.5, 2.0], 0.03, grid)
+        res.append((tot, ll.copy(), mean.copy(), var.copy(), ev.h2d_bytes))
+    assert res[0][0] == res[1][0] and all(np.array_equal(res[0][i], res[1][i]) for i in (1, 2, 3))
+    assert res[0][4] - res[1][4] == b * n * 8                    # one double per data point less on the wire
+
+
 def test_moments_on_device(cg):
     """cgp_moments_dev (the norm.fit of the pulls without a download) against numpy, any size and alignment."""
     import torch
