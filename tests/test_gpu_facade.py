@@ -123,6 +123,44 @@ def test_build_pull_modes(cg):
     assert_close(bc._pull[len(ys) + 1], split(r["pullB"], off)[1], 1e-8, 1e-11)
 
 
+def test_streamed_evaluator_other_shapes(cg):
+    """The pipelined evaluator beyond the one-warp kernels: 100-point objects (generic kernel), 2D objects,
+    likelihood only (no grid), optional inputs left out, a batch smaller than one chunk."""
+    from cosmogp_b200.batch import DeviceBatch, StreamedEvaluator
+    rng = np.random.default_rng(9)
+    # N = 100 -> one 4-warp CTA per object
+    b, n, m = 300, 100, 24
+    x = np.sort(rng.uniform(0, 60, (b, n)), axis=1); y = rng.standard_normal((b, n)); ye = np.full((b, n), 0.3)
+    grid = np.linspace(0, 60, m)
+    ev = StreamedEvaluator(b, n, m, n_chunks=3, n_streams=2)
+    for k, v in (("x", x), ("y", y), ("y0", 0.0), ("y_err", ye), ("new_y0", 0.0)):
+        ev.host(k)[...] = v
+    tot, ll, mean, var, info = ev.run([0.7, 3.0], 0.02, grid)
+    batch = DeviceBatch(x.ravel(), y.ravel(), np.arange(b + 1) * n, y_err=ye.ravel())
+    t2, ll2, _ = batch.log_likelihood([0.7, 3.0], 0.02)
+    m2, v2, _ = batch.predict([0.7, 3.0], 0.02, grid)
+    assert np.array_equal(ll, ll2) and tot == t2 and not info.any()
+    assert_close(mean, m2, 1e-10, 1e-11); assert_close(var, v2, 1e-10, 1e-11)
+    # 2D objects
+    b, n, m = 257, 30, 20
+    xy = rng.uniform(0, 10, (b, n, 2)); z = rng.standard_normal((b, n)); ze = np.full((b, n), 0.2)
+    g2 = rng.uniform(0, 10, (m, 2)); h2 = [1.0, 2.0, 1.5, 0.3]
+    ev = StreamedEvaluator(b, n, m, dim=2, n_chunks=2, n_streams=2)
+    for k, v in (("x", xy), ("y", z), ("y0", 0.0), ("y_err", ze), ("new_y0", 0.0)):
+        ev.host(k)[...] = v
+    tot, ll, mean, var, info = ev.run(h2, 0.05, g2)
+    batch = DeviceBatch(xy.reshape(-1, 2), z.ravel(), np.arange(b + 1) * n, y_err=ze.ravel(), dim=2)
+    _, ll2, _ = batch.log_likelihood(h2, 0.05)
+    m2, v2, _ = batch.predict(h2, 0.05, g2)
+    assert np.array_equal(ll, ll2) and np.array_equal(mean, m2) and np.array_equal(var, v2)
+    # likelihood only
+    ev = StreamedEvaluator(b, n, 0, dim=2, n_chunks=2, n_streams=2)
+    for k, v in (("x", xy), ("y", z), ("y0", 0.0), ("y_err", ze)):
+        ev.host(k)[...] = v
+    tot, ll3, mean, var, info = ev.run(h2, 0.05, np.zeros((0, 2)))
+    assert np.array_equal(ll3, ll2) and mean.shape == (b, 0)
+
+
 def test_mean_spline_on_device(cg):
     """cgp_spline_mean_dev = scipy's InterpolatedUnivariateSpline (FITPACK splev) + per-object offset, including
     extrapolation beyond the template; and the streamed evaluator computing y0 from it instead of uploading it."""
