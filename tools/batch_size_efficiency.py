@@ -1,27 +1,41 @@
 """ns per object of the resident fused step (factor+LL kernel, uniform-grid prediction kernel) vs batch size:
-how much a chunk-sized launch loses to kernel tails (explains the end-to-end leg's compute time)."""
+how much a chunk-sized launch loses (explains the end-to-end leg's compute time).  Buffers are allocated once."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
+from cosmogp_b200 import _lib
 from cosmogp_b200.batch import DeviceBatch
+L = _lib.lib()
 out = {}
-g = torch.from_numpy(np.linspace(-10, 40, bench.M_GRID)).cuda()
+M = bench.M_GRID
+g = torch.from_numpy(np.linspace(-10, 40, M)).cuda()
+hyp = np.ascontiguousarray(bench.HYP, dtype=np.float64)
+BMAX = 100000
+x, y, ye, tmean, ymean = bench.make_c2(BMAX, 2)
+full = DeviceBatch(x.ravel(), y.ravel(), np.arange(BMAX + 1, dtype=np.int64) * bench.N_EPOCH, y_err=ye.ravel(), dim=1)
+stride = int(L.cgp_factor_ws_doubles(bench.N_EPOCH))
+ws = torch.empty(BMAX * stride, dtype=torch.float64, device="cuda")
+ll = torch.empty(BMAX, dtype=torch.float64, device="cuda"); info = torch.empty(BMAX, dtype=torch.int32, device="cuda")
+mean = torch.empty(BMAX * M, dtype=torch.float64, device="cuda"); var = torch.empty_like(mean)
+st = torch.cuda.current_stream().cuda_stream
+p = lambda t: t.data_ptr()
 for B in (2048, 4096, 8192, 16384, 32768, 65536, 100000):
-    x, y, ye, tmean, ymean = bench.make_c2(B, 2)
-    batch = DeviceBatch(x.ravel(), y.ravel(), np.arange(B + 1, dtype=np.int64) * bench.N_EPOCH, y_err=ye.ravel(), dim=1)
-    def step():
-        fac = batch.factor_dev(bench.HYP, bench.NUGGET, want_ll=True)
-        return batch.predict_factored_dev(fac, g, None, None, True, uniform_grid=False)
-    for _ in range(3): step()
-    torch.cuda.synchronize()
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    reps = 10
-    tf = tp = 0.0
-    for _ in range(reps):
-        e[0].record(); fac = batch.factor_dev(bench.HYP, bench.NUGGET, want_ll=True); e[1].record()
-        batch.predict_factored_dev(fac, g, None, None, True, uniform_grid=False); e[2].record()
+    def factor():
+        _lib.check(L.cgp_factor_batched_dev(B, p(full.off), bench.N_EPOCH, 1, p(full.x), p(full.y), None, p(full.y_err),
+                                            _lib.hptr(hyp), bench.NUGGET, 0.0, 0, p(ws), p(ll), p(info), st), "factor")
+    def grid(flags):
+        _lib.check(L.cgp_predict_factored_dev(B, p(full.off), bench.N_EPOCH, 1, p(full.x), _lib.hptr(hyp), bench.NUGGET, flags,
+                                              p(ws), p(info), p(g), None, M, None, p(mean), p(var), st), "grid")
+    res = {}
+    for name, fn in (("factor", factor), ("grid_general", lambda: grid(0)), ("grid_uniform", lambda: grid(_lib.CGP_GRID_UNIFORM))):
+        for _ in range(3): fn()
         torch.cuda.synchronize()
-        tf += e[0].elapsed_time(e[1]); tp += e[1].elapsed_time(e[2])
-    out[B] = {"factor_ns_per_object": tf / reps * 1e6 / B, "grid_general_ns_per_object": tp / reps * 1e6 / B}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps): fn()
+        e1.record(); torch.cuda.synchronize()
+        res[name + "_ns_per_object"] = e0.elapsed_time(e1) / reps * 1e6 / B
+    out[B] = res
 print(json.dumps(out))
