@@ -319,6 +319,48 @@ def test_c2_full_size_ll_against_batched_oracle(L):
     assert np.array_equal(ll2, ll[perm])
 
 
+def test_c2_full_size_prediction(L):
+    """BASELINE config 2 at full size, prediction side: 10^5 x 60 on a 100-point grid with a shared mean.  A sample of
+    objects against the batched oracle (1e-9); the uniform-grid kernel against the general one on every object;
+    a permuted batch gives the permuted result bit for bit; the likelihood emitted by the factor kernel against the
+    LL kernel; the pipelined host-resident evaluator gives the resident results bit for bit."""
+    import torch
+    from cosmogp_b200.batch import DeviceBatch, StreamedEvaluator
+    rng = np.random.default_rng(6)
+    b, n, m = 100000, 60, 100
+    x = np.sort(rng.uniform(-10, 40, (b, n)), axis=1); ye = np.full((b, n), 0.2)
+    diff = rng.normal(0, 0.3, b)
+    y0 = -18 + 2 * np.sin(x / 10) + diff[:, None]
+    y = y0 + 0.5 * rng.standard_normal((b, n))
+    grid = np.linspace(-10, 40, m); tmpl = -18 + 2 * np.sin(grid / 10)
+    hyp, nug = [0.5, 2.0], 0.0
+    off = np.arange(b + 1, dtype=np.int64) * n
+    batch = DeviceBatch(x.ravel(), y.ravel(), off, y0=y0.ravel(), y_err=ye.ravel())
+    fac = batch.factor_dev(hyp, nug, want_ll=True)
+    g = torch.from_numpy(grid).cuda(); packed = torch.from_numpy(np.concatenate([tmpl, diff])).cuda()
+    mu, vu, _ = batch.predict_factored_dev(fac, g, None, packed, True, template_mean=True, uniform_grid=True)
+    mg, vg, _ = batch.predict_factored_dev(fac, g, None, packed, True, template_mean=True, uniform_grid=False)
+    mu = mu.cpu().numpy().reshape(b, m); vu = vu.cpu().numpy().reshape(b, m)
+    assert_close(mu, mg.cpu().numpy().reshape(b, m), 1e-10, 1e-10); assert_close(vu, vg.cpu().numpy().reshape(b, m), 1e-10, 1e-11)
+    sel = rng.choice(b, 256, replace=False)
+    mo, vo = O.predict_batched_1d(x[sel], y[sel], y0[sel], ye[sel], hyp, nug, grid, tmpl[None, :] + diff[sel, None])
+    assert_close(mu[sel], mo, RTOL, 1e-11); assert_close(vu[sel], vo, RTOL, 1e-12)
+    _, ll, _ = batch.log_likelihood(hyp, nug)
+    assert_close(fac["ll"].cpu().numpy(), ll, 1e-13, 1e-11)
+    perm = rng.permutation(b)
+    b2 = DeviceBatch(x[perm].ravel(), y[perm].ravel(), off, y0=y0[perm].ravel(), y_err=ye[perm].ravel())
+    f2 = b2.factor_dev(hyp, nug)
+    p2 = torch.from_numpy(np.concatenate([tmpl, diff[perm]])).cuda()
+    m2, v2, _ = b2.predict_factored_dev(f2, g, None, p2, True, template_mean=True, uniform_grid=True)
+    assert np.array_equal(m2.cpu().numpy().reshape(b, m), mu[perm]) and np.array_equal(v2.cpu().numpy().reshape(b, m), vu[perm])
+    ev = StreamedEvaluator(b, n, m, n_chunks=8, n_streams=4, shared_mean=True)
+    for k, v in (("x", x), ("y", y), ("y0", y0), ("y_err", ye), ("template", tmpl), ("diff", diff)):
+        ev.host(k)[...] = v
+    tot, lls, ms, vs, infos = ev.run(hyp, nug, grid)
+    assert not infos.any() and np.array_equal(ms, mu) and np.array_equal(vs, vu)
+    assert np.array_equal(lls, fac["ll"].cpu().numpy()) and tot == float(np.add.accumulate(lls)[-1])
+
+
 def test_c5_pulls_against_batched_oracle(L):
     """BASELINE config 5 recipe (N = 40, y_err = 0.1) on 20,000 of the 10^6 objects: closed-form LOO pulls
     against the batched oracle; and pulls of a Gaussian process drawn from the model are ~N(0,1)."""
