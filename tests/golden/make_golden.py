@@ -261,8 +261,47 @@ def notebooks():
          printed_single=np.array([0.64033549419520619, 2.0650717053156979, 0.0833030775856]))
 
 
+# ----------------------------------------------------------------- 8. constructor mean options
+def mean_options():
+    """Gaussian_process.py:171-186: substract_mean=True without a template (y0 = mean(y) per object), and a
+    template with the offsets `diff` handed in; likelihood and prediction (own epochs and a shared grid)."""
+    rng = np.random.default_rng(11)
+    b = 7
+    hyp = np.array([0.6, 2.5]); nug = 0.04
+    xs = [np.sort(rng.uniform(-5, 35, int(n))) for n in rng.integers(8, 40, b)]
+    yes = [rng.uniform(0.05, 0.3, len(x)) for x in xs]
+    ys = [3.0 + 0.5 * i + np.sin(x / 3.0) + 0.2 * rng.standard_normal(len(x)) for i, x in enumerate(xs)]
+    grid = np.linspace(-6, 36, 41)
+    out = {}
+    with ref_loader.quiet():
+        gp = ref.gaussian_process_nobject(ys, xs, y_err=yes, substract_mean=True)
+        gp.hyperparameters = hyp
+        out["ll_sub"] = ll_of(gp, hyp, nug, False)
+        out["y0_sub"] = flat([np.ones(len(xs[i])) * gp.y0[i] for i in range(b)])[0]
+        gp.get_prediction(new_binning=grid, svd_method=False)
+        out["mean_sub"] = np.array(gp.Prediction, dtype=float)
+        out["var_sub"] = np.array([np.diag(c) for c in gp.covariance_matrix])
+        tm = np.linspace(-8, 38, 30); ym = 3.0 + np.sin(tm / 3.0)
+        diff = list(0.5 * np.arange(b) + 0.05 * rng.standard_normal(b))
+        gd = ref.gaussian_process_nobject(ys, xs, y_err=yes, Mean_Y=ym, Time_mean=tm, diff=diff)
+        gd.hyperparameters = hyp
+        out["ll_diff"] = ll_of(gd, hyp, nug, False)
+        gd.get_prediction(new_binning=grid, svd_method=False)
+        out["mean_diff"] = np.array(gd.Prediction, dtype=float)
+        out["var_diff"] = np.array([np.diag(c) for c in gd.covariance_matrix])
+        g1 = ref.gaussian_process(ys[2], xs[2], y_err=yes[2], Mean_Y=ym, Time_mean=tm)     # single object, own epochs
+        g1.hyperparameters = hyp
+        out["ll_one"] = ll_of(g1, hyp, nug, False)
+        g1.get_prediction(new_binning=None, svd_method=False)
+        out["mean_one"] = np.array(g1.Prediction[0], dtype=float)
+        out["var_one"] = np.diag(g1.covariance_matrix[0])
+    x, off = flat(xs)
+    save("mean_options", x=x, y=flat(ys)[0], y_err=flat(yes)[0], off=off, hyp=hyp, nugget=nug, grid=grid,
+         mean_x=tm, mean_y=ym, diff=np.array(diff), **out)
+
+
 if __name__ == "__main__":
     np.seterr(all="ignore")
-    which = sys.argv[1:] or ["kat_1d", "kat_2d", "c1_single", "ragged_1d", "pulls_1d", "batch_2d", "notebooks"]
+    which = sys.argv[1:] or ["kat_1d", "kat_2d", "c1_single", "ragged_1d", "pulls_1d", "batch_2d", "notebooks", "mean_options"]
     for w in which:
         globals()[w]()

@@ -83,6 +83,41 @@ def test_nobject_shared_mean_workflow(cg):
     assert_close(g1.covariance_matrix[0], g["own_cov0"], 1e-9, 1e-12)
 
 
+def test_constructor_mean_options(cg):
+    """substract_mean=True without a template, template + given offsets, single object at its own epochs:
+    the facade against the real reference's outputs (tests/golden/mean_options.npz)."""
+    g = golden("mean_options")
+    off, hyp, nug, grid = g["off"], g["hyp"], float(g["nugget"]), g["grid"]
+    xs, ys, yes = (split(g[k], off) for k in ("x", "y", "y_err"))
+    gp = cg.gaussian_process_nobject(ys, xs, y_err=yes, substract_mean=True)
+    assert_close(np.concatenate(gp.y0), g["y0_sub"], 1e-15)
+    gp.hyperparameters = hyp.copy(); gp.nugget = nug
+    gp.compute_log_likelihood(hyp, svd_method=False)
+    assert_close(gp.log_likelihood[0], g["ll_sub"], 1e-9)
+    gp.get_prediction(new_binning=grid, svd_method=False)
+    assert_close(np.array(gp.Prediction), g["mean_sub"], 1e-9); assert_close(np.array(gp.prediction_variance), g["var_sub"], 1e-9, 1e-13)
+    gd = cg.gaussian_process_nobject(ys, xs, y_err=yes, Mean_Y=g["mean_y"], Time_mean=g["mean_x"], diff=list(g["diff"]))
+    gd.hyperparameters = hyp.copy(); gd.nugget = nug
+    gd.compute_log_likelihood(hyp, svd_method=False)
+    assert_close(gd.log_likelihood[0], g["ll_diff"], 1e-9)
+    gd.get_prediction(new_binning=grid, COV='diag', svd_method=False)
+    assert_close(np.array(gd.Prediction), g["mean_diff"], 1e-9); assert_close(np.array(gd.prediction_variance), g["var_diff"], 1e-9, 1e-13)
+    assert_close(np.asarray(gd.warning_pf)[3], O_mean_on_grid(g, 3), 1e-14)
+    g1 = cg.gaussian_process(ys[2], xs[2], y_err=yes[2], Mean_Y=g["mean_y"], Time_mean=g["mean_x"])
+    g1.hyperparameters = hyp.copy(); g1.nugget = nug
+    g1.compute_log_likelihood(hyp, svd_method=False)
+    assert_close(g1.log_likelihood[0], g["ll_one"], 1e-9)
+    g1.get_prediction(svd_method=False)
+    assert_close(g1.Prediction[0], g["mean_one"], 1e-9); assert_close(np.diag(g1.covariance_matrix[0]), g["var_one"], 1e-9, 1e-13)
+
+
+def O_mean_on_grid(g, i):
+    from oracle import gp_oracle as O
+    off = g["off"]
+    xs, ys = split(g["x"], off), split(g["y"], off)
+    return O.return_mean_1d(ys[i], xs[i], g["mean_y"], g["mean_x"], diff=g["diff"][i], new_x=g["grid"])
+
+
 def test_notebook_fits(cg):
     """docs/notebook/1D_kernel_example_with_noise.ipynb cells 9 and 21."""
     g = golden("notebook_with_noise")

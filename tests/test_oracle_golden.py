@@ -88,6 +88,34 @@ def test_ragged_1d_shared_mean():
     assert_close(O.norm_fit(g["pullB"]), [g["pullB_avg"], g["pullB_std"]], 1e-12)
 
 
+def test_mean_options():
+    """Constructor mean options run by the real reference: substract_mean=True without a template, a template with
+    the offsets handed in, a single object predicted at its own epochs."""
+    g = golden("mean_options")
+    off, hyp, nug, grid = g["off"], g["hyp"], float(g["nugget"]), g["grid"]
+    xs, ys, yes, y0sub = (split(g[k], off) for k in ("x", "y", "y_err", "y0_sub"))
+    b = len(xs)
+    # substract_mean=True, no template: y0 = mean(y) and that constant is also the mean on the grid
+    for i in range(b):
+        assert_close(O.return_mean_1d(ys[i], xs[i]), y0sub[i][0], 1e-15)          # a scalar per object (mean.py:87-90)
+    assert_close(O.log_likelihood_sum(ys, xs, hyp, nug, yes, y0sub), g["ll_sub"], RT)
+    for i in range(b):
+        m, v = O.predict(ys[i], xs[i], hyp, nug, grid, yes[i], y0sub[i], y0sub[i][0], full_cov=False)
+        assert_close(m, g["mean_sub"][i], RT); assert_close(v, g["var_sub"][i], RT, 1e-13)
+    # template + given offsets
+    y0d = [O.return_mean_1d(ys[i], xs[i], g["mean_y"], g["mean_x"], diff=g["diff"][i]) for i in range(b)]
+    assert_close(O.log_likelihood_sum(ys, xs, hyp, nug, yes, y0d), g["ll_diff"], RT)
+    for i in range(b):
+        ny0 = O.return_mean_1d(ys[i], xs[i], g["mean_y"], g["mean_x"], diff=g["diff"][i], new_x=grid)
+        m, v = O.predict(ys[i], xs[i], hyp, nug, grid, yes[i], y0d[i], ny0, full_cov=False)
+        assert_close(m, g["mean_diff"][i], RT); assert_close(v, g["var_diff"][i], RT, 1e-13)
+    # one object, template, offset estimated, own epochs
+    y01 = O.return_mean_1d(ys[2], xs[2], g["mean_y"], g["mean_x"])
+    assert_close(O.log_likelihood(ys[2], xs[2], hyp, nug, yes[2], y01), g["ll_one"], RT)
+    m, v = O.predict(ys[2], xs[2], hyp, nug, xs[2], yes[2], y01, y01, full_cov=False)
+    assert_close(m, g["mean_one"], RT); assert_close(v, g["var_one"], RT, 1e-13)
+
+
 def test_pulls_modes_a_d():
     g = golden("pulls_1d")
     hyp, nug = g["hyp"], float(g["nugget"])
