@@ -261,6 +261,23 @@ def notebooks():
          printed_single=np.array([0.64033549419520619, 2.0650717053156979, 0.0833030775856]))
 
 
+# ----------------------------------------------------------------- 7b. joint 2D fit
+def fit_2d():
+    """find_hyperparameters on three 2D objects (Gaussian_process.py:216-253).  At HEAD the 2D likelihood does not
+    depend on sigma (quirk Q2), so only l_x, l_y, l_xy and the likelihood at the optimum are meaningful."""
+    g = np.load(os.path.join(HERE, "batch_2d.npz"))
+    off = g["off"]
+    xs = [g["x"][off[i]:off[i + 1]] for i in range(3)]; ys = [g["y"][off[i]:off[i + 1]] for i in range(3)]
+    yes = [g["y_err"][off[i]:off[i + 1]] for i in range(3)]
+    guess = [1.0, 40.0, 40.0, 10.0]
+    with ref_loader.quiet():
+        gp = ref.gaussian_process_nobject(ys, xs, kernel="RBF2D", y_err=yes)
+        gp.find_hyperparameters(hyperparameter_guess=guess, svd_method=False)
+        fit = np.array(gp.hyperparameters, dtype=float)
+        ll = ll_of(gp, fit, 0.0, False)
+    save("fit_2d", guess=np.array(guess), fit_hyp=fit, ll_at_fit=ll)
+
+
 # ----------------------------------------------------------------- 8. constructor mean options
 def mean_options():
     """Gaussian_process.py:171-186: substract_mean=True without a template (y0 = mean(y) per object), and a
@@ -302,6 +319,6 @@ def mean_options():
 
 if __name__ == "__main__":
     np.seterr(all="ignore")
-    which = sys.argv[1:] or ["kat_1d", "kat_2d", "c1_single", "ragged_1d", "pulls_1d", "batch_2d", "notebooks", "mean_options"]
+    which = sys.argv[1:] or ["kat_1d", "kat_2d", "c1_single", "ragged_1d", "pulls_1d", "batch_2d", "notebooks", "fit_2d", "mean_options"]
     for w in which:
         globals()[w]()

@@ -273,6 +273,20 @@ def test_2d_objects(cg):
     assert_close(bp.pull, g["pull2"], 1e-9, 1e-12)
 
 
+def test_2d_joint_fit(cg):
+    """find_hyperparameters on 2D objects against the real reference's optimum.  The 2D likelihood does not depend on
+    sigma at HEAD (quirk Q2), so Nelder-Mead drifts along sigma: the length scales and the likelihood are compared."""
+    g, f = golden("batch_2d"), golden("fit_2d")
+    off = g["off"]
+    xs, ys, yes = split(g["x"], off), split(g["y"], off), split(g["y_err"], off)
+    gp = cg.gaussian_process_nobject(ys, xs, kernel="RBF2D", y_err=yes)
+    gp.find_hyperparameters(hyperparameter_guess=list(f["guess"]), svd_method=False)
+    gp.compute_log_likelihood(gp.hyperparameters, svd_method=False)
+    print("2D fit", gp.hyperparameters, gp.log_likelihood[0], "reference", f["fit_hyp"], float(f["ll_at_fit"]))
+    assert_close(gp.log_likelihood[0], float(f["ll_at_fit"]), 1e-6)
+    assert_close(gp.hyperparameters[1:], f["fit_hyp"][1:], 2e-3)
+
+
 def test_not_positive_definite_raises_linalgerror(cg):
     x = np.array([0.0, 1.0, 1.0, 2.0]); y = np.array([0.1, 0.2, 0.3, 0.4])
     gp = cg.gaussian_process(y, x)
