@@ -28,6 +28,7 @@ M_GRID = 100
 HYP = (0.5, 2.0)
 NUGGET = 0.0
 YERR = 0.2
+N_CHECK = 32            # objects per rank whose timed-step outputs are checked against the oracle
 
 
 def flops_ll(n):            # build + POTRF + forward solve + norms
@@ -93,59 +94,94 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU arm
+def reference_available():
+    from oracle import ref_loader
+    return ref_loader.available()
+
+
 def _cpu_worker(args):
-    """One host core: the oracle port of the reference per-object path
-    (log_likelihood_gp with cholesky_inverse + get_prediction mean/variance diagonal)."""
-    x, y, y0, ye, grid, ny0 = args
+    """One host core, one BLAS thread.  kind "reference": the UNMODIFIED reference (baseline/_ref, loaded by
+    oracle/ref_loader.py) through its own public API -- gaussian_process_nobject(...).compute_log_likelihood(hyp)
+    then .get_prediction(new_binning=grid, COV=True) (cosmogp/Gaussian_process.py:191-213, :270-361; COV=True is the
+    only way the reference yields a predictive variance).  kind "port": the oracle restatement of the same calls
+    (fallback when baseline/_ref is absent).  Only the two calls are timed, not the construction of the object."""
+    kind, svd, x, y, ye, tmean, ymean, grid = args
     from threadpoolctl import threadpool_limits
-    from oracle import gp_oracle as O
     with threadpool_limits(limits=1):
+        if kind == "reference":
+            from oracle import ref_loader
+            ref = ref_loader.load()
+            with ref_loader.quiet():
+                gp = ref.gaussian_process_nobject(list(y), list(x), kernel="RBF1D", y_err=list(ye), Mean_Y=ymean, Time_mean=tmean)
+                gp.hyperparameters = np.array(HYP); gp.nugget = NUGGET; gp.fit_nugget = False
+                t0 = time.perf_counter()
+                gp.compute_log_likelihood(np.array(HYP), svd_method=svd)
+                gp.get_prediction(new_binning=grid, COV=True, svd_method=svd)
+                var0 = np.diag(gp.covariance_matrix[0]).copy()
+                dt = time.perf_counter() - t0
+            return dt, float(np.ravel(gp.log_likelihood)[0]), gp.Prediction[0].copy(), var0
+        from oracle import gp_oracle as O
+        from cosmogp_b200 import mean as M
+        off = np.arange(len(x) + 1, dtype=np.int64) * x.shape[1]
+        y0, d = M.batched_mean(x.ravel(), y.ravel(), off, 1, ymean, tmean, None)
+        y0 = y0.reshape(x.shape)
+        ny0 = M.template_on_grid(grid, 1, ymean, tmean)[None, :] + d[:, None]
         t0 = time.perf_counter()
         acc = 0.0
         for i in range(len(x)):
-            acc += O.log_likelihood(y[i], x[i], HYP, NUGGET, ye[i], y0[i])
-            m, v = O.predict(y[i], x[i], HYP, NUGGET, grid, ye[i], y0[i], ny0[i], full_cov=False)
-            acc += m[0] + v[0]
-        return time.perf_counter() - t0, acc
+            acc += O.log_likelihood(y[i], x[i], HYP, NUGGET, ye[i], y0[i], svd_method=svd)
+            m, v = O.predict(y[i], x[i], HYP, NUGGET, grid, ye[i], y0[i], ny0[i], full_cov=False, svd_method=svd)
+            if i == 0:
+                m0, v0 = m, v
+        return time.perf_counter() - t0, acc, m0, v0
 
 
-def cpu_pass(x, y, y0, ye, grid, ny0, pool, cores):
-    """All host cores, one process each, objects split evenly.  Returns objects/s."""
-    parts = np.array_split(np.arange(len(x)), cores)
-    t0 = time.perf_counter()
-    pool.map(_cpu_worker, [(x[p], y[p], y0[p], ye[p], grid, ny0[p]) for p in parts])
-    return len(x) / (time.perf_counter() - t0)
+def cpu_pass(kind, svd, x, y, ye, tmean, ymean, grid, pool, cores):
+    """All host cores, one process each, objects split evenly; the pass takes as long as its slowest worker.
+    Returns (objects/s, per-worker results)."""
+    parts = [p for p in np.array_split(np.arange(len(x)), cores) if len(p)]
+    res = pool.map(_cpu_worker, [(kind, svd, x[p], y[p], ye[p], tmean, ymean, grid) for p in parts])
+    return len(x) / max(r[0] for r in res), res
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the step on this box's host cores."""
     if rank != 0:
         return
     import multiprocessing as mp
-    from cosmogp_b200 import mean as M
     cores = os.cpu_count() or 1
+    kind = "reference" if reference_available() else "port"
     per_step = args.cpu_objects or 400 * cores
     x, y, ye, tmean, ymean = make_c2(per_step, 2)
-    off = np.arange(per_step + 1, dtype=np.int64) * N_EPOCH
-    y0, d = M.batched_mean(x.ravel(), y.ravel(), off, 1, ymean, tmean, None)
-    y0 = y0.reshape(per_step, N_EPOCH)
     grid = np.linspace(-10, 40, M_GRID)
-    ny0 = M.template_on_grid(grid, 1, ymean, tmean)[None, :] + d[:, None]
+    if kind == "reference":
+        from oracle import ref_loader
+        ref_loader.load()                                   # imported once, inherited by the forked workers
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_pass(x, y, y0, ye, grid, ny0, pool, cores)
-        t0 = time.perf_counter()
+            cpu_pass(kind, False, x, y, ye, tmean, ymean, grid, pool, cores)
+        dt = 0.0
         for _ in range(args.steps):
-            cpu_pass(x, y, y0, ye, grid, ny0, pool, cores)
-        dt = time.perf_counter() - t0
+            v, _r = cpu_pass(kind, False, x, y, ye, tmean, ymean, grid, pool, cores)
+            dt += per_step / v
+        v_svd, _r = cpu_pass(kind, True, x, y, ye, tmean, ymean, grid, pool, cores)
     val = per_step * args.steps / dt
-    sample = "%d of the 10^5 objects per step (N=%d, M=%d), oracle port, %d processes x 1 BLAS thread" % (
-        per_step, N_EPOCH, M_GRID, cores)
+    what = ("unmodified PFLeget/cosmogp from baseline/_ref: gaussian_process_nobject.compute_log_likelihood + "
+            "get_prediction(COV=True), svd_method=False" if kind == "reference" else
+            "oracle port of the same calls (baseline/_ref absent), svd_method=False")
+    sample = ("%d of the 10^5 objects of the workload per step (N=%d, M=%d), objects/s = sample / slowest worker, no "
+              "extrapolation beyond that (the path is linear in the number of objects); %s; %d processes x 1 BLAS thread"
+              % (per_step, N_EPOCH, M_GRID, what, cores))
+    cfg = workload_config(100000, 1)
+    cfg["cpu_sample_objects_per_step"] = per_step
     print(json.dumps({
         "impl": "reference", "metric": "gp_fits_per_sec", "value": val, "unit": "objects/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(per_step, 1),
-        "cpu_baseline": {"value": val, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "objects/s", "cores": cores, "kind": kind, "sample": sample,
+                         "svd_method_true": {"value": v_svd, "unit": "objects/s",
+                                             "what": "the same pass with svd_method=True (the reference's default argument)"}},
         "e2e": {"value": val, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -224,7 +260,6 @@ def main():
     for _ in range(args.warmup):
         out = step()
     torch.cuda.synchronize()
-    ll_first = out[0][:64].cpu().numpy()         # checked against the CPU leg's oracle values below
 
     sampler = ClockSampler(local); sampler.start()
     time.sleep(0.3)
@@ -236,9 +271,19 @@ def main():
     for k in range(args.steps):
         ev[k][0].record()
         e_mid, e_mid2 = ev[k][1], ev[k][2]
-        step()
+        out = step()
         ev[k][3].record()
     torch.cuda.synchronize()
+    # parity of the TIMED step, on every rank: LL, mean and variance of the first N_CHECK objects against the oracle
+    from oracle import gp_oracle as O              # the checker, never the thing measured
+    y0m = y0.reshape(B, N_EPOCH)
+    sel = slice(0, N_CHECK)
+    ll_o = O.ll_batched_1d(x[sel], y[sel], y0m[sel], ye[sel], HYP, NUGGET)
+    mean_o, var_o = O.predict_batched_1d(x[sel], y[sel], y0m[sel], ye[sel], HYP, NUGGET, grid, ny0[sel])
+    chk = {"ll": out[0][:N_CHECK].cpu().numpy(), "mean": out[1][:N_CHECK * M_GRID].cpu().numpy().reshape(N_CHECK, M_GRID),
+           "var": out[2][:N_CHECK * M_GRID].cpu().numpy().reshape(N_CHECK, M_GRID)}
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.abs(b)))
+    parity = max(rel(chk["ll"], ll_o), rel(chk["mean"], mean_o), rel(chk["var"], var_o))
     launches = _lib.lib().cgp_launch_count() - launches0
     if world > 1:
         dist.barrier()
@@ -291,6 +336,12 @@ def main():
         h2d, d2h, _ = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    parity = max(parity, rel(ev_e2e.host("ll")[sel], ll_o), rel(ev_e2e.host("mean")[sel], mean_o), rel(ev_e2e.host("var")[sel], var_o))
+    if world > 1:
+        t = torch.tensor([parity], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity = float(t.item())
+    assert parity < 1e-9, "rank %d: parity check of the timed step failed: %g" % (rank, parity)
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -339,23 +390,34 @@ def main():
                                     "achieved": (flops_ll(N_EPOCH) + flops_predict(N_EPOCH, M_GRID)) * B * args.steps
                                     / (total_ms * 1e-3) * 1e-12}},
     }
+    line["parity_max_rel_err"] = parity
+    line["parity"] = ("every rank: LL, mean and variance of %d objects of its timed resident step and of its end-to-end "
+                      "step against the numpy oracle; max relative error over ranks, asserted < 1e-9" % N_CHECK)
     if not args.no_cpu and world == 1:
         import multiprocessing as mp
         cores = os.cpu_count() or 1
+        kind = "reference" if reference_available() else "port"
         n_cpu = args.cpu_objects or 1000 * cores
+        if kind == "reference":
+            from oracle import ref_loader
+            ref_loader.load()
         with mp.get_context("fork").Pool(cores) as pool:
-            y0m = y0.reshape(B, N_EPOCH)
-            cpu_pass(x[:4 * cores], y[:4 * cores], y0m[:4 * cores], ye[:4 * cores], grid, ny0[:4 * cores], pool, cores)
-            v = cpu_pass(x[:n_cpu], y[:n_cpu], y0m[:n_cpu], ye[:n_cpu], grid, ny0[:n_cpu], pool, cores)
-        # the CPU leg doubles as the checker: the timed GPU step's likelihoods of the first objects against the port
-        from oracle import gp_oracle as O
-        ref = O.ll_batched_1d(x[:64], y[:64], y0m[:64], ye[:64], HYP, NUGGET)
-        parity = float(np.max(np.abs(ll_first - ref) / np.abs(ref)))
-        assert parity < 1e-9, "parity check failed: %g" % parity
-        line["parity_max_rel_err_ll"] = parity
-        line["cpu_baseline"] = {"value": v, "unit": "objects/s", "cores": cores, "kind": "port",
-                                "sample": "first %d of the %d objects, one pass (LL + predict mean/var-diag per object), "
-                                          "oracle port, %d processes x 1 BLAS thread" % (n_cpu, B, cores)}
+            cpu_pass(kind, False, x[:4 * cores], y[:4 * cores], ye[:4 * cores], tmean, ymean, grid, pool, cores)
+            v, res = cpu_pass(kind, False, x[:n_cpu], y[:n_cpu], ye[:n_cpu], tmean, ymean, grid, pool, cores)
+            v_svd, _r = cpu_pass(kind, True, x[:n_cpu // 2], y[:n_cpu // 2], ye[:n_cpu // 2], tmean, ymean, grid, pool, cores)
+        # the CPU leg doubles as a second checker: object 0's prediction by the reference itself against the timed step
+        m_ref, v_ref = res[0][2], res[0][3]
+        line["parity_vs_cpu_arm"] = float(max(np.max(np.abs(chk["mean"][0] - m_ref) / np.abs(m_ref)),
+                                              np.max(np.abs(chk["var"][0] - v_ref) / np.abs(v_ref))))
+        assert line["parity_vs_cpu_arm"] < 1e-9, "object 0 differs from the CPU arm: %g" % line["parity_vs_cpu_arm"]
+        line["cpu_baseline"] = {"value": v, "unit": "objects/s", "cores": cores, "kind": kind,
+                                "sample": "first %d of the %d objects, one pass (compute_log_likelihood + get_prediction with "
+                                          "COV=True per object, svd_method=False), %s, %d processes x 1 BLAS thread, "
+                                          "objects/s = sample / slowest worker" % (
+                                              n_cpu, B, "unmodified reference from baseline/_ref" if kind == "reference"
+                                              else "oracle port (baseline/_ref absent)", cores),
+                                "svd_method_true": {"value": v_svd, "unit": "objects/s",
+                                                    "what": "the reference's default argument, %d objects" % (n_cpu // 2)}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

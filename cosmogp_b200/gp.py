@@ -4,11 +4,16 @@ arguments, methods, attributes and error behaviour; numpy in, numpy out.  The
 per-object Python loops of the reference (:207, :264, :304, :349) are replaced by
 single batched launches on a device-resident copy of the data.
 
-Differences, all supersets:
-  * `svd_method` is accepted everywhere but both values run the device Cholesky path
-    (north_star keeps the SVD only as a host-side reference check, inv_matrix.svd_inverse);
-    a non-positive-definite K therefore raises numpy.linalg.LinAlgError like the
-    reference's svd_method=False path (inv_matrix.py:23) instead of pseudo-inverting.
+Differences:
+  * `svd_method`: every object is factorised by the device Cholesky kernels whatever the flag says (for a
+    positive-definite K the two reference paths agree to rounding).  They differ when an object's K is NOT
+    numerically positive definite (noise-free data, duplicate epochs): with svd_method=False the call raises
+    numpy.linalg.LinAlgError like the reference (inv_matrix.py:23); with svd_method=True (the reference's
+    default) exactly those objects -- the ones whose device factorisation reported info != 0 -- are redone by
+    the host reference check `inv_matrix.svd_inverse` (pseudo-inverse above s = 1e-15 and log det over the
+    kept singular values, inv_matrix.py:4-18), so the call never raises, as in the reference.  A K that is
+    positive definite in floating point but has singular values below 1e-15 keeps its Cholesky result where
+    the reference would truncate (tests/test_gpu_facade.py::test_svd_method_* pin both behaviours).
   * `get_prediction(COV='diag')` computes only the variance diagonal
     (`prediction_variance`); COV=True keeps `covariance_matrix`, materialised per object
     on access.  `kernel_matrix` / `inv_kernel_matrix` are materialised on access too.
@@ -79,7 +84,7 @@ class Gaussian_process:
 
         self._dim = 1 if kernel == 'RBF1D' else 2
         self.kernel = rbf_kernel_1d if kernel == 'RBF1D' else rbf_kernel_2d
-        sigma, L = init_rbf(Time, y)                                        # :145-146, :153-154
+        sigma, L = init_rbf(Time, y) if len(y) else (np.nan, np.nan)         # :145-146, :153-154 (empty: a rank's shard)
         self.hyperparameters = np.array([sigma, L]) if self._dim == 1 else np.array([sigma, L, L, 0.])
 
         self.y = y
@@ -144,10 +149,12 @@ class Gaussian_process:
         import torch.distributed as dist
         if not (self._dist and dist.is_initialized() and dist.get_world_size() > 1):
             return list(per_object_arrays)
-        width = per[0] if per else 0                      # equal-length outputs (shared grid)
+        # equal-length outputs (shared grid); the width comes from the grid, not from the local objects (a rank may own none)
+        width = 0 if self.as_the_same_time else len(self.new_binning)
+        assert width and all(p == width for p in per), "gather() needs a prediction on a shared grid"
         ranges = sharding.balanced_ranges(self._all_sizes, dist.get_world_size())
         counts = [(r[1] - r[0]) * width for r in ranges]
-        allflat = sharding.gather_ragged(flat, counts, device=self.batch.device)
+        allflat = sharding.gather_ragged(flat, counts, device=self._device)
         return list(allflat.reshape(-1, width)) if width else []
 
     # ------------------------------------------------------------------ device state
@@ -161,8 +168,15 @@ class Gaussian_process:
     @property
     def _is_large(self):
         """Objects beyond the shared-memory path (N > 224) go one by one through the HBM-resident
-        blocked factorisation (cosmogp_b200.dense.LargeObject)."""
-        return len(self._off) > 1 and int(np.diff(self._off).max()) > _lib.CGP_SMALL_MAX_N
+        blocked factorisation (cosmogp_b200.dense.LargeObject).  Sharded objects decide from the sizes of ALL
+        objects, so that every rank takes the same branch (and the same collectives)."""
+        sizes = self._all_sizes if self._dist else np.diff(self._off)
+        return len(sizes) > 0 and int(np.max(sizes)) > _lib.CGP_SMALL_MAX_N
+
+    @property
+    def _device(self):
+        import torch
+        return torch.device("cuda", torch.cuda.current_device())
 
     def _large_objects(self):
         if getattr(self, "_large", None) is None:
@@ -194,20 +208,60 @@ class Gaussian_process:
             Nugget = self.nugget
             hyperparameter = Hyperparameter
         if self._is_large:
-            per_object = np.array([o.factor(hyperparameter, Nugget) for o in self._large_objects()])
-            self.log_likelihood_per_object = per_object
-            self.log_likelihood = np.array([float(np.add.accumulate(per_object)[-1])])
-            return
-        total, per_object, info = self.batch.log_likelihood(hyperparameter, Nugget, flags=self.flags)
+            per_object, info = np.zeros(self.N_sn), np.zeros(self.N_sn, dtype=np.int32)
+            for i, o in enumerate(self._large_objects()):
+                try:
+                    per_object[i] = o.factor(hyperparameter, Nugget)
+                except np.linalg.LinAlgError:
+                    info[i] = 1
+            total = None
+        else:
+            total, per_object, info = self.batch.log_likelihood(hyperparameter, Nugget, flags=self.flags)
+        if info.any() and svd_method:                       # the reference's default never raises (inv_matrix.py:4-18)
+            per_object = np.array(per_object, dtype=float)
+            for i in np.nonzero(info)[0]:
+                per_object[i] = self._svd_object(int(i), hyperparameter, Nugget)[0]
+            info = np.zeros_like(info)
+            total = None
+        if total is None:                                   # left to right, like the loop at :205-213
+            total = float(np.add.accumulate(per_object)[-1]) if len(per_object) else 0.0
         if self._dist:
             from . import sharding
-            bad = sharding.allreduce_sum(float(np.count_nonzero(info)), device=self.batch.device)
+            bad = sharding.allreduce_sum(float(np.count_nonzero(info)), device=self._device)
             if bad:
                 raise np.linalg.LinAlgError("%d object(s) with a covariance that is not positive definite" % int(bad))
-            total = sharding.allreduce_sum(total, device=self.batch.device)
+            total = sharding.allreduce_sum(total, device=self._device)
         self._raise_if_bad(info)
         self.log_likelihood_per_object = per_object
         self.log_likelihood = np.array([total])             # shape (1,), quirk Q5
+
+    def _svd_object(self, i, hyperparameter, nugget, grid=None, new_y0=0.0, want_var=False):
+        """ONE object through the host reference check (inv_matrix.svd_inverse): used only for objects whose
+        device Cholesky reported a non-positive pivot, and only when the caller asked for svd_method=True.
+        -> (log-likelihood, mean on `grid` or None, variance diagonal or None), formulas of
+        Gaussian_process.py:59-73 and :332-361."""
+        import warnings
+        from .inv_matrix import svd_inverse
+        o0, o1 = int(self._off[i]), int(self._off[i + 1])
+        x, y = self._x_flat[o0:o1], self._y_flat[o0:o1]
+        ye = None if self._ye_flat is None else self._ye_flat[o0:o1]
+        r = y - (self._y0_flat[o0:o1] if self._y0_flat is not None else 0.0)
+        kw = {"flags": self.flags} if self._dim == 2 else {}
+        hyp = np.asarray(hyperparameter, dtype=float)
+        warnings.warn("covariance of object %d is not positive definite: pseudo-inverse by the host SVD reference "
+                      "check (svd_method=True, cosmogp/inv_matrix.py:4-18)" % i, RuntimeWarning, stacklevel=3)
+        inv, logdet = svd_inverse(self.kernel(x, hyp, nugget=nugget, y_err=ye, **kw), return_logdet=True)
+        w = inv @ r
+        ll = -0.5 * float(r @ w) - 0.5 * len(r) * np.log(2 * np.pi) - 0.5 * logdet
+        if grid is None:
+            return ll, None, None
+        h = self.kernel(x, hyp, new_x=grid)
+        mean = h @ w + new_y0
+        var = None
+        if want_var:
+            amp = hyp[0] ** 2 if (self._dim == 1 or self.flags & _lib.CGP_AMP_ON_AUTOCOV) else 1.0
+            var = amp + nugget ** 2 - ((h @ inv) * h).sum(axis=1)
+        return ll, mean, var
 
     def find_hyperparameters(self, hyperparameter_guess=None, nugget=False, svd_method=True):
         """Maximum likelihood with scipy.optimize.fmin on the host (:216-253); every
@@ -273,9 +327,9 @@ class Gaussian_process:
     def compute_kernel_matrix(self):
         """kernel_matrix[sn] = K(Time[sn]) with nugget and y_err (:256-267), on access."""
         hyp, nug = np.array(self.hyperparameters, dtype=float), float(self.nugget)
-        self.kernel_matrix = _LazyMatrices(self.N_sn, lambda i: self._object_matrices(i, hyp, nug)[0])
+        self.kernel_matrix = _LazyMatrices(self.N_sn, lambda i: self._object_matrices(i, hyp, nug, True)[0])
 
-    def _object_matrices(self, i, hyp, nug):
+    def _object_matrices(self, i, hyp, nug, svd=False):
         o0, o1 = self._off[i], self._off[i + 1]
         sub = DeviceBatch(self._x_flat[o0:o1], self._y_flat[o0:o1], np.array([0, o1 - o0], dtype=np.int64),
                           y_err=None if self._ye_flat is None else self._ye_flat[o0:o1], dim=self._dim)
@@ -283,6 +337,9 @@ class Gaussian_process:
             from . import dense
             return dense.object_matrices(sub, hyp, nug, self.flags)
         k, kinv, info = sub.matrices(hyp, nug, flags=self.flags)
+        if info.any() and svd:                              # inv_kernel_matrix of the reference's default path (:319-320)
+            from .inv_matrix import svd_inverse
+            return k[0], svd_inverse(k[0])
         self._raise_if_bad(info)
         return k[0], kinv[0]
 
@@ -300,7 +357,7 @@ class Gaussian_process:
             hyp_b, nug_b = self.hyperparameters_per_object, self.nugget_per_object
         has_mean = self.substract_mean or self.Mean_Y is not None
         self.compute_kernel_matrix()
-        self.inv_kernel_matrix = _LazyMatrices(self.N_sn, lambda i: self._object_matrices(i, hyp, nug)[1])
+        self.inv_kernel_matrix = _LazyMatrices(self.N_sn, lambda i: self._object_matrices(i, hyp, nug, bool(svd_method))[1])
         want_var = bool(COV)
 
         if self._is_large:
@@ -310,7 +367,13 @@ class Gaussian_process:
             self.Prediction, self.prediction_variance = [], ([] if want_var else None)
             for i, obj in enumerate(self._large_objects()):
                 o0, o1 = self._off[i], self._off[i + 1]
-                obj.factor(hyp, nug)
+                try:
+                    obj.factor(hyp, nug)
+                    failed = False
+                except np.linalg.LinAlgError:
+                    if not svd_method:
+                        raise
+                    failed = True
                 if new_binning is None:
                     grid, ny0 = self._x_flat[o0:o1], (self._y0_flat[o0:o1] if has_mean else None)
                 else:
@@ -319,7 +382,10 @@ class Gaussian_process:
                     if has_mean:
                         tmpl = _mean.template_on_grid(grid, self._dim, self.Mean_Y, self.Time_mean)
                         ny0 = (tmpl if tmpl is not None else 0.0) + self._diff_used[i] * np.ones(len(grid))
-                m, v = obj.predict(grid, new_y0=ny0, want_var=want_var)
+                if failed:
+                    _, m, v = self._svd_object(i, hyp, nug, grid, 0.0 if ny0 is None else ny0, want_var)
+                else:
+                    m, v = obj.predict(grid, new_y0=ny0, want_var=want_var)
                 self.Prediction.append(m)
                 if want_var:
                     self.prediction_variance.append(v)
@@ -334,6 +400,13 @@ class Gaussian_process:
             new_y0 = self._y0_flat if has_mean else None                   # :308-309
             mean, var, info = self.batch.predict(hyp_b if per_object else hyp, nug_b if per_object else nug, grid,
                                                  goff=goff, new_y0=new_y0, want_var=want_var, flags=self.flags)
+            if info.any() and svd_method and not per_object:
+                for i in np.nonzero(info)[0]:
+                    sl = slice(int(goff[i]), int(goff[i + 1]))
+                    _, mean[sl], v = self._svd_object(int(i), hyp, nug, grid[sl], new_y0[sl] if has_mean else 0.0, want_var)
+                    if want_var:
+                        var[sl] = v
+                info = np.zeros_like(info)
             self._raise_if_bad(info)
             self.Prediction = RaggedView(mean, goff)
             self.prediction_variance = RaggedView(var, goff) if want_var else None
@@ -351,6 +424,13 @@ class Gaussian_process:
                 new_y0 = _LazyMeanOnGrid(*mean_template)
             mean, var, info = self.batch.predict(hyp_b if per_object else hyp, nug_b if per_object else nug, grid,
                                                  mean_template=mean_template, want_var=want_var, flags=self.flags)
+            if info.any() and svd_method and not per_object:
+                for i in np.nonzero(info)[0]:
+                    ny0 = (mean_template[0] + mean_template[1][i]) if has_mean else 0.0
+                    _, mean[i], v = self._svd_object(int(i), hyp, nug, grid, ny0, want_var)
+                    if want_var:
+                        var[i] = v
+                info = np.zeros_like(info)
             self._raise_if_bad(info)
             self.Prediction = list(mean)
             self.prediction_variance = list(var) if want_var else None

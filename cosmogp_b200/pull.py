@@ -128,20 +128,3 @@ class build_pull:
         if not self._results:
             return None
         return self._results[-1]["batch"]._down(self._results[-1]["prediction_variance"])
-
-    def plot_result(self, binning=60):
-        """Histogram of the pulls with the fitted normal law (pull.py:105-140)."""
-        import pylab as plt
-        from scipy.stats import norm as normal
-        plt.figure()
-        plt.hist(self.pull, bins=binning, density=True)
-        xmin, xmax = plt.xlim()
-        _max = max([abs(xmin), abs(xmax)])
-        plt.xlim(-_max, _max)
-        xaxis = np.linspace(-_max, _max, 100)
-        plt.plot(xaxis, normal.pdf(xaxis, self.pull_average, self.pull_std), 'r', linewidth=3)
-        plt.title(r"Fit results: $\mu$ = $ %.2f \pm %.2f $, $\sigma$ = $ %.2f \pm %.2f $" % (
-            self.pull_average, self.pull_std / np.sqrt(len(self.pull)),
-            self.pull_std, self.pull_std / np.sqrt(2 * len(self.pull))))
-        plt.ylabel('Number of points (normed)')
-        plt.xlabel('Pull')

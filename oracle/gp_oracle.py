@@ -145,7 +145,26 @@ def predict(y, x, hyp, nugget, grid, y_err=None, y0=0.0, new_y0=0.0, kind="1d",
     if full_cov:
         return mean, kern(grid, hyp, nugget=nugget) - h @ (inv @ h.T)
     amp2 = hyp[0] ** 2 if kind == "1d" else 1.0             # 2D auto branch has no sigma^2 (Q2)
-    return mean, amp2 + nugget ** 2 - np.einsum("mn,nk,mk->m", h, inv, h)
+    return mean, amp2 + nugget ** 2 - ((h @ inv) * h).sum(axis=1)   # diag(H K^-1 H^T) through BLAS
+
+
+def predict_grid_chunked(y, x, hyp, nugget, grid, y_err=None, y0=0.0, new_y0=0.0, kind="1d", chunk=2000):
+    """mean and diag(covariance) on a grid too long for the M x M covariance (BASELINE config 3: M = 10^5 would
+    need 80 GB): the grid goes through Gaussian_process.py:332-335 / :356-361 in slices of `chunk` points with ONE
+    inverse (inv_matrix.py:21-31) -- the chunking the reference's own DES notebook applies (cell 9)."""
+    kern = rbf_1d if kind == "1d" else rbf_2d
+    inv = cholesky_inverse(kern(x, hyp, nugget=nugget, y_err=y_err))
+    w = inv @ (np.asarray(y, dtype=float) - y0)
+    grid = np.asarray(grid, dtype=float)
+    m = len(grid)
+    ny0 = np.broadcast_to(np.asarray(new_y0, dtype=float), (m,))
+    amp2 = hyp[0] ** 2 if kind == "1d" else 1.0
+    mean, var = np.empty(m), np.empty(m)
+    for s in range(0, m, chunk):
+        h = kern(x, hyp, new_x=grid[s:s + chunk])
+        mean[s:s + chunk] = h @ w + ny0[s:s + chunk]
+        var[s:s + chunk] = amp2 + nugget ** 2 - ((h @ inv) * h).sum(axis=1)
+    return mean, var
 
 
 # --------------------------------------------------------------------------- leave-one-out pulls

@@ -9,6 +9,11 @@ the order cosmogp/__init__.py:12-25 imports them.  Nothing is copied into the re
 loader is used by tests/golden/make_golden.py (fixture generation) and by the
 `-m "not gpu"` tests that pin oracle/gp_oracle.py against the real reference;
 those tests skip when the path is absent.  The product never imports this file.
+
+On the GPU box the same unmodified sources are found under baseline/_ref (the offline
+pip install of the reference done by baseline/fetch_ref.py: git-ignored, shipped by
+gpurun); bench.py's CPU arm (--impl reference, cpu_baseline) times them from there.
+Search order: $COSMOGP_REFERENCE_ROOT, /root/reference, <repo>/baseline/_ref.
 """
 import contextlib
 import importlib.machinery
@@ -19,7 +24,18 @@ import re
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("COSMOGP_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    cands = [os.environ.get("COSMOGP_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "cosmogp", "__init__.py")):
+            return c
+    return cands[0] or cands[1]
+
+
+REFERENCE_ROOT = _find_root()
 _PRINT_STMT = re.compile(r"^(\s*)print (.*)$", re.M)
 _ORDER = ["inv_matrix", "mean", "Gaussian_process", "kernel", "pull"]
 

@@ -261,6 +261,49 @@ def notebooks():
          printed_single=np.array([0.64033549419520619, 2.0650717053156979, 0.0833030775856]))
 
 
+# ----------------------------------------------------------------- 7a. the reference's DEFAULT path (svd_method=True)
+def svd_default():
+    # docs/notebook/1D_kernel_example_without_noise.ipynb cells 1,3,7,9,11: noise-free single object, default arguments
+    np.random.seed(1)
+    grids, ys = [], []
+    for _ in range(100):
+        n_point = int(np.random.uniform(25, 30))
+        grid = np.linspace(-10, 30, n_point)
+        k = ref.rbf_kernel_1d(grid, np.array([0.5, 1]), nugget=0)
+        ys.append(np.random.multivariate_normal(np.zeros_like(grid), k))
+        grids.append(grid)
+    gp = ref.gaussian_process(ys[0], grids[0])
+    gp.find_hyperparameters(hyperparameter_guess=[0.5, 1])
+    fit = np.array(gp.hyperparameters, dtype=float)
+    new_grid = np.linspace(-10, 30, 60)
+    gp.get_prediction(new_binning=new_grid)
+    # a numerically SINGULAR covariance: duplicated epochs, no noise -> Cholesky fails, the default path pseudo-inverts
+    rng = np.random.default_rng(12)
+    xs = np.repeat(np.sort(rng.uniform(0, 10, 12)), 2)
+    yv = np.sin(xs) + 0.01 * rng.standard_normal(len(xs))
+    xg = np.sort(rng.uniform(0, 10, 17)); yg = np.sin(xg)           # a well-posed companion object
+    hyp = np.array([0.8, 1.5])
+    g2 = ref.gaussian_process_nobject([yv, yg], [xs, xg], y_err=[np.zeros(len(xs)), np.full(len(xg), 0.1)])
+    g2.hyperparameters = hyp
+    ll_svd = ll_of(g2, hyp, 0.0, True)
+    with ref_loader.quiet():
+        per = per_object_ll([yv, yg], [xs, xg], ref.rbf_kernel_1d, hyp, 0.0, [np.zeros(len(xs)), np.full(len(xg), 0.1)],
+                            [0.0, 0.0], svd_method=True)
+    grid2 = np.linspace(0, 10, 9)
+    with ref_loader.quiet():
+        g2.get_prediction(new_binning=grid2, COV=True, svd_method=True)
+    chol_fails = False
+    try:
+        ll_of(g2, hyp, 0.0, False)
+    except np.linalg.LinAlgError:
+        chol_fails = True
+    assert chol_fails
+    save("svd_default", x=grids[0], y=ys[0], fit_single=fit, printed_single=np.array([0.54652372907962654, 1.228403962377433]),
+         new_grid=new_grid, pred=np.array(gp.Prediction[0]), var=np.diag(gp.covariance_matrix[0]),
+         sing_x=xs, sing_y=yv, ok_x=xg, ok_y=yg, sing_hyp=hyp, sing_ll_total=ll_svd, sing_ll_per_object=per,
+         sing_grid=grid2, sing_pred=np.array(g2.Prediction), sing_var=np.array([np.diag(c) for c in g2.covariance_matrix]))
+
+
 # ----------------------------------------------------------------- 7b. joint 2D fit
 def fit_2d():
     """find_hyperparameters on three 2D objects (Gaussian_process.py:216-253).  At HEAD the 2D likelihood does not
@@ -319,6 +362,6 @@ def mean_options():
 
 if __name__ == "__main__":
     np.seterr(all="ignore")
-    which = sys.argv[1:] or ["kat_1d", "kat_2d", "c1_single", "ragged_1d", "pulls_1d", "batch_2d", "notebooks", "fit_2d", "mean_options"]
+    which = sys.argv[1:] or ["kat_1d", "kat_2d", "c1_single", "ragged_1d", "pulls_1d", "batch_2d", "notebooks", "fit_2d", "mean_options", "svd_default"]
     for w in which:
         globals()[w]()

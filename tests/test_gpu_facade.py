@@ -294,6 +294,52 @@ def test_not_positive_definite_raises_linalgerror(cg):
         gp.compute_log_likelihood([1.0, 1.0], svd_method=False)
 
 
+def test_svd_method_default_on_the_noise_free_notebook(cg):
+    """The reference's DEFAULT arguments (svd_method=True) on its noise-free notebook
+    (docs/notebook/1D_kernel_example_without_noise.ipynb cells 7-11): fitted hyperparameters as printed there, prediction
+    and variance against the fixture made by the real reference.  K is noise free but positive definite along the
+    whole simplex path, so the device Cholesky serves every evaluation."""
+    g = golden("svd_default")
+    gp = cg.gaussian_process(g["y"], g["x"])
+    gp.find_hyperparameters(hyperparameter_guess=[0.5, 1])
+    assert_close(gp.hyperparameters, g["printed_single"], 1e-4)
+    gp.hyperparameters = list(g["fit_single"])
+    gp.get_prediction(new_binning=g["new_grid"])
+    assert_close(gp.Prediction[0], g["pred"], 1e-7, 1e-9)
+    assert_close(gp.prediction_variance[0], g["var"], 1e-6, 1e-9)      # noise-free: variances down to 1e-16 at the data
+
+
+def test_svd_method_default_on_a_singular_covariance(cg):
+    """Duplicated epochs without noise: the reference's default path pseudo-inverts (inv_matrix.py:4-18) and never
+    raises; svd_method=False raises LinAlgError (inv_matrix.py:23).  Here the object whose device factorisation
+    reports a non-positive pivot is redone by the host SVD reference check when svd_method=True; the well-posed
+    companion object keeps its device result."""
+    import warnings
+    g = golden("svd_default")
+    ys, xs = [g["sing_y"], g["ok_y"]], [g["sing_x"], g["ok_x"]]
+    yes = [np.zeros(len(g["sing_x"])), np.full(len(g["ok_x"]), 0.1)]
+    gp = cg.gaussian_process_nobject(ys, xs, y_err=yes)
+    gp.hyperparameters = list(g["sing_hyp"])
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.compute_log_likelihood(g["sing_hyp"], svd_method=False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        gp.compute_log_likelihood(g["sing_hyp"])                        # default: svd_method=True
+        assert any("SVD reference check" in str(m.message) for m in w)
+    assert_close(gp.log_likelihood_per_object[1], g["sing_ll_per_object"][1], 1e-9)
+    assert_close(gp.log_likelihood_per_object[0], g["sing_ll_per_object"][0], 1e-6)   # 12 singular values truncated
+    assert_close(gp.log_likelihood[0], float(g["sing_ll_total"]), 1e-6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gp.get_prediction(new_binning=g["sing_grid"], COV='diag')
+    assert_close(gp.Prediction[1], g["sing_pred"][1], 1e-9)
+    assert_close(gp.prediction_variance[1], g["sing_var"][1], 1e-9)
+    assert_close(gp.Prediction[0], g["sing_pred"][0], 1e-5, 1e-7)
+    assert_close(gp.prediction_variance[0], g["sing_var"][0], 0.0, 1e-5)     # ~1e-7 numbers made of rounding noise
+    with pytest.raises(np.linalg.LinAlgError):
+        gp.get_prediction(new_binning=g["sing_grid"], COV='diag', svd_method=False)
+
+
 def test_streamed_evaluator_matches_resident_batch(cg):
     """The pipelined end-to-end path (chunks over 3 streams) returns bit-identical results."""
     from cosmogp_b200.batch import DeviceBatch, StreamedEvaluator

@@ -118,3 +118,53 @@ def test_c3_shape_psf_interpolation(D):
     mean, var = obj.predict(grid)
     mo, vo = O.predict(y, x, hyp, 0.0, grid[:300], ye, kind="2d", full_cov=False)
     assert_close(mean[:300], mo, 1e-9, 1e-11); assert_close(var[:300], vo, 1e-9, 1e-12)
+
+
+def test_c3_full_size_psf_interpolation(D):
+    """BASELINE config 3 at its full size: 2D, 2,000 stars (SURVEY 8d recipe, seed 3), mean and variance on ALL 10^5
+    grid points against the chunked oracle (Gaussian_process.py:332-361 in 2,000-point slices)."""
+    rng = np.random.default_rng(3)
+    n, m = 2000, 100000
+    x = rng.uniform(-200, 200, (n, 2)); hyp = [1.0, 30.0, 25.0, 50.0]
+    ye = np.full(n, 0.2); y = np.cos(x[:, 0] / 60) * np.sin(x[:, 1] / 45) + 0.2 * rng.standard_normal(n)
+    grid = rng.uniform(-200, 200, (m, 2))
+    obj = D.LargeObject(x, y, ye, None, dim=2)
+    ll = obj.factor(hyp, 0.0)
+    assert_close(ll, O.log_likelihood(y, x, hyp, 0.0, ye, kind="2d"), 1e-9)
+    mean, var = obj.predict(grid)
+    mo, vo = O.predict_grid_chunked(y, x, hyp, 0.0, grid, ye, kind="2d", chunk=2000)
+    assert mean.shape == (m,) and var.shape == (m,)
+    assert_close(mean, mo, 1e-9, 1e-11, "C3 mean"); assert_close(var, vo, 1e-9, 1e-12, "C3 variance")
+
+
+def test_c4_large_single_object_at_config_size(D):
+    """BASELINE config 4 at its full size: one 2D object of N = 20,000 points (SURVEY 8d recipe, seed 4:
+    X ~ U(0,1000)^2, hyp = [1, 30, 30, 0], y_err = 0.3).  log det, the quadratic form, alpha = K^-1 r and the
+    likelihood of the blocked device Cholesky against scipy's LAPACK path on the host -- the calls the reference makes
+    at cosmogp/inv_matrix.py:21-31 and Gaussian_process.py:68-73 (cho_solve instead of the explicit inverse:
+    the same numbers, a third of the host time).  Tolerance: relative 1e-9 (cond(K) <= 2.2e5)."""
+    from scipy import linalg as sla
+    rng = np.random.default_rng(4)
+    n = 20000
+    x = rng.uniform(0, 1000, (n, 2)); hyp = [1.0, 30.0, 30.0, 0.0]
+    ye = np.full(n, 0.3)
+    y = np.sin(x[:, 0] / 90) * np.cos(x[:, 1] / 70) + 0.3 * rng.standard_normal(n)
+    obj = D.LargeObject(x, y, ye, None, dim=2)
+    ll = obj.factor(hyp, 0.0)
+    alpha = obj.alpha[:n].cpu().numpy()
+    # host covariance row block by row block (kernel.py:127-151; sigma = 1, so the sigma^2 quirk Q2 is moot)
+    k = np.empty((n, n))
+    for s in range(0, n, 2000):
+        k[s:s + 2000] = O.rbf_2d(x, hyp, new_x=x[s:s + 2000])
+    k[np.arange(n), np.arange(n)] = 1.0 + ye ** 2
+    assert_close(k[:300, :300], O.rbf_2d(x[:300], hyp, y_err=ye[:300]), 1e-15, 1e-300, "host K assembly")
+    low = sla.cholesky(k, lower=True, overwrite_a=True, check_finite=False)
+    del k
+    logdet = 2.0 * np.sum(np.log(np.diag(low)))                       # inv_matrix.py:28
+    a_ref = sla.cho_solve((low, True), y, check_finite=False)
+    quad = float(y @ a_ref)
+    ll_ref = -0.5 * quad - 0.5 * n * np.log(2 * np.pi) - 0.5 * logdet    # Gaussian_process.py:68-73
+    assert_close(obj.logdet, logdet, 1e-9, what="C4 logdet")
+    assert_close(obj.quad, quad, 1e-9, what="C4 quadratic form")
+    assert_close(ll, ll_ref, 1e-9, what="C4 log-likelihood")
+    assert_close(alpha, a_ref, 1e-9, 1e-9 * np.abs(a_ref).max(), "C4 alpha")

@@ -195,3 +195,34 @@ def test_oracle_vs_live_reference_random():
         k = O.rbf_1d(x, hyp, nugget=0.1, y_err=ye)
         assert_close(O.cholesky_inverse(k), ref.cholesky_inverse(k), 1e-15, 1e-15)
         assert_close(O.svd_inverse(k), ref.svd_inverse(k), 1e-15, 1e-15)
+
+
+def test_chunked_grid_prediction_equals_the_one_shot_formula():
+    """predict_grid_chunked (used for BASELINE config 3 at full size) = predict(full_cov=False) slice by slice."""
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-50, 50, (70, 2)); y = rng.standard_normal(70); ye = np.full(70, 0.2)
+    grid = rng.uniform(-50, 50, (333, 2)); hyp = [1.2, 20.0, 15.0, 30.0]
+    m1, v1 = O.predict(y, x, hyp, 0.1, grid, ye, 0.0, 0.0, kind="2d", full_cov=False)
+    m2, v2 = O.predict_grid_chunked(y, x, hyp, 0.1, grid, ye, kind="2d", chunk=100)
+    assert np.max(np.abs(m1 - m2)) < 1e-12 and np.max(np.abs(v1 - v2)) < 1e-12
+    x1 = np.sort(rng.uniform(0, 30, 40)); g1 = np.linspace(0, 30, 77)
+    m1, v1 = O.predict(y[:40], x1, [0.7, 3.0], 0.05, g1, ye[:40], 0.1, 0.2, full_cov=False)
+    m2, v2 = O.predict_grid_chunked(y[:40], x1, [0.7, 3.0], 0.05, g1, ye[:40], 0.1, 0.2, chunk=20)
+    assert np.max(np.abs(m1 - m2)) < 1e-12 and np.max(np.abs(v1 - v2)) < 1e-12
+
+
+def test_oracle_svd_path_against_the_reference_default():
+    """The oracle's svd_method=True branch (inv_matrix.py:4-18) on the fixture the real reference produced with its
+    default arguments: a singular covariance (12 singular values truncated) beside a well-posed one."""
+    g = golden("svd_default")
+    ll0 = O.log_likelihood(g["sing_y"], g["sing_x"], g["sing_hyp"], 0.0, np.zeros(len(g["sing_x"])), svd_method=True)
+    ll1 = O.log_likelihood(g["ok_y"], g["ok_x"], g["sing_hyp"], 0.0, np.full(len(g["ok_x"]), 0.1), svd_method=True)
+    assert_close(ll0, g["sing_ll_per_object"][0], 1e-9); assert_close(ll1, g["sing_ll_per_object"][1], 1e-12)
+    assert_close(ll0 + ll1, float(g["sing_ll_total"]), 1e-12)
+    with pytest.raises(np.linalg.LinAlgError):
+        O.log_likelihood(g["sing_y"], g["sing_x"], g["sing_hyp"], 0.0, np.zeros(len(g["sing_x"])), svd_method=False)
+    m, v = O.predict(g["ok_y"], g["ok_x"], g["sing_hyp"], 0.0, g["sing_grid"], np.full(len(g["ok_x"]), 0.1), svd_method=True, full_cov=False)
+    assert_close(m, g["sing_pred"][1], 1e-10); assert_close(v, g["sing_var"][1], 1e-9)
+    # the noise-free notebook fit (default arguments) is reproduced by the oracle's objective
+    r = fmin(lambda h: -O.log_likelihood(g["y"], g["x"], h, 0.0, svd_method=True), [0.5, 1], disp=False)
+    assert_close(np.abs(r), g["printed_single"], 1e-12)
