@@ -250,6 +250,29 @@ class DeviceBatch:
         _lib.check(rc, "cgp_predict_batched_dev")
         return mean[:nout], (var[:nout] if want_var else None), self._info[:self.n_obj]
 
+    def step_dev(self, hyp, nugget, grid, goff=None, new_y0=None, want_var=True, floor=0.0, flags=0,
+                 template_mean=False, uniform_grid=False, out=None):
+        """One pass of the hot path (cgp_step_batched_dev): log-likelihood AND prediction at the same hyperparameters
+        from ONE factorisation per object.  grid / goff / new_y0 are device tensors as in predict_dev; template_mean,
+        uniform_grid as in predict_factored_dev.  out: optional dict of preallocated device tensors "ll", "mean", "var".
+        -> (ll_obj, mean, var, info) device tensors."""
+        h = self._hyp(hyp)
+        m = 0 if goff is not None else int(grid.shape[0])
+        nout = int(goff[-1].item()) if goff is not None else self.n_obj * m
+        new = lambda n: torch.empty(max(n, 1), dtype=torch.float64, device=self.device)
+        ll = out["ll"] if out else new(self.n_obj)
+        mean = out["mean"] if out else new(nout)
+        var = (out["var"] if out else new(nout)) if want_var else None
+        fl = int(flags) | (_lib.CGP_MEAN_TEMPLATE if template_mean else 0) | (_lib.CGP_GRID_UNIFORM if uniform_grid else 0)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_step_batched_dev(self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x),
+                                                 self._p(self.y), self._p(self.y0), self._p(self.y_err), _lib.hptr(h),
+                                                 float(nugget), float(floor), fl, self._p(grid), self._p(goff), m,
+                                                 self._p(new_y0), self._p(ll), self._p(mean), self._p(var),
+                                                 self._p(self._info), self._stream())
+        _lib.check(rc, "cgp_step_batched_dev")
+        return ll[:self.n_obj], mean[:nout], (var[:nout] if want_var else None), self._info[:self.n_obj]
+
     def factor_dev(self, hyp, nugget=0.0, floor=0.0, flags=0, want_ll=False):
         """Factorise every object once (objects of <= 64 points): returns an opaque device workspace
         holding inv(L) and alpha, reusable by predict_factored_dev for any number of grids.

@@ -267,7 +267,7 @@ static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
                         const double* hyp, const double* hyp_obj, const double* nugget_obj,
                         double nugget, double floor, unsigned flags,
                         const double* xnew, const int64_t* goff, int64_t m_shared,
-                        const double* new_y0, double* mean, double* var, int* info, void* stream) {
+                        const double* new_y0, double* ll_obj, double* mean, double* var, int* info, void* stream) {
   if (n_obj < 0 || (n_obj && (!off || !x || !y || !xnew || !mean || !info)))
     return fail(CGP_ERR_ARG, "cgp_predict_batched_dev: NULL argument");
   if (!goff && m_shared < 0) return fail(CGP_ERR_ARG, "cgp_predict_batched_dev: m_shared < 0");
@@ -297,12 +297,22 @@ static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
     if (want > 1) split = (int)want;
   }
   a.split = split;
-  // Many small objects with variances: two kernels.  FACTOR (latency-bound factorisation, L^-1 and
-  // alpha spilled to a workspace) then PREDICT_F (every warp in the DMMA-dense grid phase, factor
-  // staged by TMA) keep the FP64 pipe busier than the fused kernel, whose warps spend half their
-  // life in the factorisation.  Chunks of objects bound the workspace (1.2 GB).
+  a.ll = ll_obj;                                          // the N <= 64 kernels emit it from the same factorisation
+  if (ll_obj && max_n > 64) {                             // the generic kernel does not: one more launch
+    SmallArgs l = a; l.split = 1;
+    if ((rc = run_small(TASK_LL, dim, max_n, l, st, "cgp_step_batched_dev (likelihood)"))) return rc;
+    a.ll = nullptr;
+  }
+  // Many small objects with variances.  Default: ONE kernel per object batch (TASK_PREDICT / TASK_PREDICT_U): each
+  // warp factorises its object and runs the grid phase from the same shared-memory tiles, so the factor never
+  // travels through HBM, and the latency-bound factorisation of one warp hides behind the DMMA-dense grid phase
+  // of its neighbours.  CGP_PREDICT_SPLIT=1 selects the two-kernel form instead (FACTOR spills L^-1 and alpha to
+  // a workspace, PREDICT_F stages them back by TMA): what factor-once / predict-many callers use.
   static int use_split = -1;
-  if (use_split < 0) { const char* e = getenv("CGP_PREDICT_SPLIT"); use_split = (e && !atoi(e)) ? 0 : 1; }
+  if (use_split < 0) { const char* e = getenv("CGP_PREDICT_SPLIT"); use_split = (e && atoi(e)) ? 1 : 0; }
+  if (!use_split && var && max_n <= 64 && n_obj >= 2048 && split == 1 && (flags & CGP_GRID_UNIFORM) && dim == 1 && !goff &&
+      !hyp_obj && m_shared >= 2 && uniform_grid_ok_dev(xnew, m_shared, hyp, st))
+    return run_small(TASK_PREDICT_U, dim, max_n, a, st, "cgp_predict_batched_dev (fused, uniform grid)");
   if (use_split && var && max_n <= 64 && n_obj >= 2048 && split == 1) {
     const int nb = max_n < 1 ? 1 : (max_n + 7) / 8;
     const int64_t stride = factor_ws_doubles(nb);
@@ -317,6 +327,7 @@ static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
       SmallArgs f = a;
       f.n_obj = n_obj - c0 < chunk ? n_obj - c0 : chunk;
       f.off = off + c0; f.info = info + c0;
+      if (ll_obj) f.ll = ll_obj + c0;
       if (goff) f.goff = goff + c0;
       else {
         f.mean = mean + c0 * m_shared; f.var = var + c0 * m_shared;
@@ -340,7 +351,17 @@ int cgp_predict_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int di
                             const double* xnew, const int64_t* goff, int64_t m_shared,
                             const double* new_y0, double* mean, double* var, int* info, void* stream) {
   return predict_impl(n_obj, off, max_n, dim, x, y, y0, y_err, hyp, nullptr, nullptr, nugget, floor, flags,
-                      xnew, goff, m_shared, new_y0, mean, var, info, stream);
+                      xnew, goff, m_shared, new_y0, nullptr, mean, var, info, stream);
+}
+
+int cgp_step_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                         const double* x, const double* y, const double* y0, const double* y_err,
+                         const double* hyp, double nugget, double floor, unsigned flags,
+                         const double* xnew, const int64_t* goff, int64_t m_shared,
+                         const double* new_y0, double* ll_obj, double* mean, double* var, int* info, void* stream) {
+  if (n_obj && !ll_obj) return fail(CGP_ERR_ARG, "cgp_step_batched_dev: ll_obj is NULL");
+  return predict_impl(n_obj, off, max_n, dim, x, y, y0, y_err, hyp, nullptr, nullptr, nugget, floor, flags,
+                      xnew, goff, m_shared, new_y0, ll_obj, mean, var, info, stream);
 }
 
 int cgp_predict_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
@@ -350,7 +371,7 @@ int cgp_predict_objhyp_dev(int64_t n_obj, const int64_t* off, int max_n, int dim
                            const double* new_y0, double* mean, double* var, int* info, void* stream) {
   if (!hyp_obj) return fail(CGP_ERR_ARG, "cgp_predict_objhyp_dev: hyp_obj is NULL");
   return predict_impl(n_obj, off, max_n, dim, x, y, y0, y_err, nullptr, hyp_obj, nugget_obj, nugget, floor, flags,
-                      xnew, goff, m_shared, new_y0, mean, var, info, stream);
+                      xnew, goff, m_shared, new_y0, nullptr, mean, var, info, stream);
 }
 
 int cgp_predict_batched_host(int64_t n_obj, const int64_t* off, int dim,

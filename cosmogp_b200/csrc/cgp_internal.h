@@ -44,7 +44,10 @@ __host__ __device__ inline Cov cov_from_hyp(int dim, const double* hyp, double n
 // TASK_FACTOR writes L^-1 (fragment-order tiles) + alpha per object to a workspace; TASK_PREDICT_F
 // predicts from that workspace (staged into shared memory by one TMA bulk copy per object).
 // TASK_PREDICT_FU: TASK_PREDICT_F for dim 1 on a uniformly spaced shared grid with l >= spacing (exps by recurrence).
-enum Task { TASK_LL = 0, TASK_PREDICT = 1, TASK_LOO = 2, TASK_MATRICES = 3, TASK_FACTOR = 4, TASK_PREDICT_F = 5, TASK_PREDICT_FU = 6 };
+// TASK_PREDICT_U: TASK_PREDICT (factorise + predict in ONE pass, nothing spilled) on a uniform shared 1D grid; like
+// TASK_PREDICT it also writes the log-likelihood of the same factorisation when SmallArgs::ll is set.
+enum Task { TASK_LL = 0, TASK_PREDICT = 1, TASK_LOO = 2, TASK_MATRICES = 3, TASK_FACTOR = 4, TASK_PREDICT_F = 5, TASK_PREDICT_FU = 6,
+            TASK_PREDICT_U = 7 };
 
 struct SmallArgs {
   int64_t n_obj;
@@ -130,6 +133,7 @@ int launch_small64_d1_t5(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d2_t4(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d2_t5(int nb, const SmallArgs& a, cudaStream_t stream);
 int launch_small64_d1_t6(int nb, const SmallArgs& a, cudaStream_t stream);
+int launch_small64_d1_t7(int nb, const SmallArgs& a, cudaStream_t stream);
 // doubles per object in the factor workspace for nb blocks of 8 points
 inline int64_t factor_ws_doubles(int nb) { return (int64_t)(nb * (nb + 1) / 2) * 64 + 8 * nb; }
 

@@ -629,6 +629,10 @@ int launch_small(Task task, int dim, int max_n, const SmallArgs& a, cudaStream_t
     if (nbm > 8 || dim != 1 || a.goff || a.hyp_obj || a.m_shared < 2) return (int)cudaErrorInvalidValue;
     return launch_small64_d1_t6(nbm, a, stream);
   }
+  if (task == TASK_PREDICT_U) {
+    if (nbm > 8 || dim != 1 || a.goff || a.hyp_obj || a.m_shared < 2) return (int)cudaErrorInvalidValue;
+    return launch_small64_d1_t7(nbm, a, stream);
+  }
   if (task == TASK_FACTOR || task == TASK_PREDICT_F) {
     if (nbm > 8) return (int)cudaErrorInvalidValue;
     if (dim == 1) return task == TASK_FACTOR ? launch_small64_d1_t4(nbm, a, stream) : launch_small64_d1_t5(nbm, a, stream);

@@ -3,9 +3,19 @@
 // straight-line code the scheduler can overlap (ncu, round 1: the generic kernel spent
 // 40 % of its issue slots waiting on dependent FP64 results and 12 % on loop/index code).
 //
-// Same algorithm and storage as cgp_small.cu (8x8 tiles in fragment order, left-looking block
-// Cholesky on DMMA, T_J = L_JJ^-1 on the diagonal slots), restructured in phases that are each
-// dense in independent FP64 work:
+// Same algorithm as cgp_small.cu (8x8 tiles, left-looking block Cholesky on DMMA, T_J = L_JJ^-1 on the
+// diagonal slots), restructured in phases that are each dense in independent FP64 work.
+//
+// Tile layout (round 2; ncu r02c: the factor kernel ran at 80 % of the SM's shared-memory wavefront rate,
+// 27 % of the wavefronts bank conflicts): element (r, c) of a tile lives in 16-byte unit
+// rho(r)*4 + ((c>>1) ^ sigma(r)), half c&1, with rho(r) = r ^ ((r>>1)&1) and sigma(r) = (r>>1)&2.  Then
+//   * lane (g,t)'s DMMA accumulator pair (row g, columns 2t, 2t+1) is ONE 16-byte unit, and the same unit is the
+//     lane's operand of both k-halves of a product X*Y^T (the two DMMAs of a tile product sum over the even and the
+//     odd k): accumulators are stored with one conflict-free STS.128, fragments loaded with one LDS.128, and a
+//     tile that was just accumulated can be fed to the next DMMA straight from its registers (the panel
+//     solve and the triangular inverse need no shared-memory round trip);
+//   * the transposed fragment (elements (2t,g), (2t+1,g)) is two conflict-free 8-byte loads.
+// Phases:
 //   K   all covariance tiles generated up front, 8 independent exp chains per lane in flight
 //   C   column J: every tile of the column accumulates its rank-8J update at once
 //       (2 (NB-J) independent DMMA chains), one parked-K subtraction, in-register diagonal
@@ -42,19 +52,30 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
       : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __host__ __device__ constexpr int slot(int i, int j) { return ((i * (i + 1)) >> 1) + j; }
-__device__ __forceinline__ int frag_off(int r, int c) { return ((r * 4 + (c & 3)) << 1) + (c >> 2); }
+__device__ __forceinline__ int tile_off(int r, int c) {
+  const int rho = r ^ ((r >> 1) & 1), sig = (r >> 1) & 2;
+  return ((rho * 4 + ((c >> 1) ^ sig)) << 1) + (c & 1);
+}
 
 struct Lane {
-  int g, t, fr, st0, st1, tr0, tr1;
+  int g, t, nat, tr0, tr1;
   __device__ explicit Lane(int lane) {
-    g = lane >> 2; t = lane & 3; fr = lane << 1;
-    st0 = frag_off(g, 2 * t); st1 = frag_off(g, 2 * t + 1);
-    tr0 = frag_off(t, g); tr1 = frag_off(4 + t, g);
+    g = lane >> 2; t = lane & 3;
+    nat = tile_off(g, 2 * t);                            // (g, 2t), (g, 2t+1): accumulator pair == operand fragment
+    tr0 = tile_off(2 * t, g); tr1 = tile_off(2 * t + 1, g);
   }
 };
 __device__ __forceinline__ double2 ld_frag(const double* tiles, int s, const Lane& L) {
-  return *reinterpret_cast<const double2*>(tiles + s * TILE + L.fr);
+  return *reinterpret_cast<const double2*>(tiles + s * TILE + L.nat);
 }
+__device__ __forceinline__ void st_frag(double* tiles, int s, const Lane& L, double v0, double v1) {
+  *reinterpret_cast<double2*>(tiles + s * TILE + L.nat) = make_double2(v0, v1);
+}
+__device__ __forceinline__ double2 ld_frag_t(const double* tiles, int s, const Lane& L) {   // fragment of the transpose
+  const double* p = tiles + s * TILE;
+  return make_double2(p[L.tr0], p[L.tr1]);
+}
+__device__ __forceinline__ double2 ld_vec2(const double* v, int i) { return *reinterpret_cast<const double2*>(v + i); }
 __device__ __forceinline__ double red_t(double v) {
   v += __shfl_xor_sync(FULL, v, 1); v += __shfl_xor_sync(FULL, v, 2); return v;
 }
@@ -119,7 +140,7 @@ constexpr int n_vec64(int task) { return task == TASK_LOO ? 6 : 1; }
 // registers per thread (grid phase: 64 accumulators + 32 fragments), 4 warps <= 128 (factorisation,
 // pulls: shared memory allows 16+ objects per SM below 56 points); hence the minimum-blocks bounds.
 template <int DIM, int TASK, int NB>
-__global__ void __launch_bounds__(32, (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU) ? 12 : 16)
+__global__ void __launch_bounds__(32, (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU || TASK == TASK_PREDICT_U) ? 12 : 16)
 gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x;
@@ -133,15 +154,16 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   double* vr = noise + LD;                 // r (LL: becomes z)
   // predict: z overwrites the (dead) noise vector and alpha overwrites r -> same footprint as LL
   constexpr bool PF = TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU;      // predict from a stored factor
-  constexpr bool UNI = TASK == TASK_PREDICT_FU;                                // ... on a uniformly spaced shared grid
-  constexpr bool PRED_LIKE = TASK == TASK_PREDICT || TASK == TASK_FACTOR || PF;
+  constexpr bool UNI = TASK == TASK_PREDICT_FU || TASK == TASK_PREDICT_U;      // ... on a uniformly spaced shared grid
+  constexpr bool FUSED = TASK == TASK_PREDICT || TASK == TASK_PREDICT_U;       // factorise and predict in one pass (no workspace)
+  constexpr bool PRED_LIKE = FUSED || TASK == TASK_FACTOR || PF;
   double* vz = PRED_LIKE ? noise : vr + LD;
   double* va = PRED_LIKE ? vr : vz + LD;
   double* vd = va + LD;
   double* v1 = vd + LD;
   double* vu = v1 + LD;
 
-  const int split = (TASK == TASK_PREDICT || PF) ? a.split : 1;
+  const int split = (FUSED || PF) ? a.split : 1;
   const int64_t n_work = (a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj) * split;
   // factor workspace of one object: NT tiles in fragment order followed by alpha (LD doubles)
   constexpr int WS = NT * TILE + LD;
@@ -275,7 +297,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       }
 #pragma unroll
       for (int u = 0; u < TPP; ++u) {
-        if (q + u < NT) { double* p0 = tiles + (q + u) * TILE; p0[L.st0] = kv[u][0]; p0[L.st1] = kv[u][1]; }
+        if (q + u < NT) st_frag(tiles, q + u, L, kv[u][0], kv[u][1]);
       }
     }
     __syncwarp();
@@ -296,20 +318,19 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           dmma(s0[i], s1[i], fa.x, fb.x); dmma(u0[i], u1[i], fa.y, fb.y);
         }
       }
-      // C = K (parked) - update
+      // C = K (parked: every lane reads back the unit it wrote) - update
 #pragma unroll
       for (int i = 0; i < NB - J; ++i) {
-        const double* p = tiles + slot(J + i, J) * TILE;
-        s0[i] = p[L.st0] - (s0[i] + u0[i]);
-        s1[i] = p[L.st1] - (s1[i] + u1[i]);
+        const double2 kk = ld_frag(tiles, slot(J + i, J), L);
+        s0[i] = kk.x - (s0[i] + u0[i]);
+        s1[i] = kk.y - (s1[i] + u1[i]);
       }
-      __syncwarp();
+      double t0, t1;
       {
-        double t0, t1, piv; int badk;
+        double piv; int badk;
         diag_factor(s0[0], s1[0], L, t0, t1, piv, badk);
-        double* p = tiles + slot(J, J) * TILE;
-        p[L.st0] = t0; p[L.st1] = t1;
-        if (TASK == TASK_LL || TASK == TASK_FACTOR) {
+        st_frag(tiles, slot(J, J), L, t0, t1);
+        if (TASK == TASK_LL || TASK == TASK_FACTOR || FUSED) {
           lp_m *= piv;
           const int hi = __double2hiint(lp_m);
           const int e = ((hi >> 20) & 0x7ff) - 1023;
@@ -318,28 +339,16 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         }
         if (badk && bad == 0) bad = 8 * J + badk;
       }
+      // L[I][J] = C[I][J] T_J^T: both operands are accumulators of this lane (see the layout note)
 #pragma unroll
-      for (int i = 1; i < NB - J; ++i) {               // park C[I][J] to re-read it as an A fragment
-        double* p = tiles + slot(J + i, J) * TILE;
-        p[L.st0] = s0[i]; p[L.st1] = s1[i];
+      for (int i = 1; i < NB - J; ++i) {
+        const double c0 = s0[i], c1 = s1[i];
+        s0[i] = 0.0; s1[i] = 0.0; u0[i] = 0.0; u1[i] = 0.0;
+        dmma(s0[i], s1[i], c0, t0); dmma(u0[i], u1[i], c1, t1);
       }
+#pragma unroll
+      for (int i = 1; i < NB - J; ++i) st_frag(tiles, slot(J + i, J), L, s0[i] + u0[i], s1[i] + u1[i]);
       __syncwarp();
-      if (J + 1 < NB) {
-        const double2 ft = ld_frag(tiles, slot(J, J), L);
-#pragma unroll
-        for (int i = 1; i < NB - J; ++i) {             // L[I][J] = C[I][J] T_J^T
-          const double2 fc = ld_frag(tiles, slot(J + i, J), L);
-          s0[i] = 0.0; s1[i] = 0.0; u0[i] = 0.0; u1[i] = 0.0;
-          dmma(s0[i], s1[i], fc.x, ft.x); dmma(u0[i], u1[i], fc.y, ft.y);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 1; i < NB - J; ++i) {
-          double* p = tiles + slot(J + i, J) * TILE;
-          p[L.st0] = s0[i] + u0[i]; p[L.st1] = s1[i] + u1[i];
-        }
-        __syncwarp();
-      }
     }
 
     if (TASK == TASK_LL) {
@@ -351,11 +360,12 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
 #pragma unroll
         for (int P = 0; P < J; ++P) {
           const double2 f = ld_frag(tiles, slot(J, P), L);
-          p = fma(f.x, vr[8 * P + L.t], p); p2 = fma(f.y, vr[8 * P + 4 + L.t], p2);
+          const double2 rv = ld_vec2(vr, 8 * P + 2 * L.t);
+          p = fma(f.x, rv.x, p); p2 = fma(f.y, rv.y, p2);
         }
         const double wv = vr[8 * J + L.g] - red_t(p + p2);
         const double2 f = ld_frag(tiles, slot(J, J), L);
-        double q = f.x * __shfl_sync(FULL, wv, L.t * 4) + f.y * __shfl_sync(FULL, wv, (4 + L.t) * 4);
+        double q = f.x * __shfl_sync(FULL, wv, L.t * 8) + f.y * __shfl_sync(FULL, wv, L.t * 8 + 4);
         q = red_t(q);
         if (L.t == 0) { vr[8 * J + L.g] = q; quad = fma(q, q, quad); }
         __syncwarp();
@@ -369,7 +379,10 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       continue;
     }
 
-    // ---------------- L^-1 in place, row by row: L^-1[I][J] = -T_I sum_{P=J..I-1} L[I][P] L^-1[P][J]
+    // ---------------- L^-1 in place, row by row, held TRANSPOSED while it is built: with Xt[J][I] = (L^-1[I][J])^T
+    //   Xt[J][I] = -(sum_{P=J..I-1} Xt[J][P] L[I][P]^T) T_I^T,   Xt[J][J] = T_J^T,
+    // every product is of the form X*Y^T on natural fragments and the bracket feeds the second product from its
+    // accumulator registers.  Slot (I,J) holds Xt[J][I] until the conversion pass below transposes it in place.
 #pragma unroll
     for (int I = 1; I < NB; ++I) {
       double s0[NB], s1[NB];
@@ -377,32 +390,35 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       for (int j = 0; j < NB; ++j) { s0[j] = 0.0; s1[j] = 0.0; }
 #pragma unroll
       for (int P = 0; P < I; ++P) {
-        const double2 fa = ld_frag(tiles, slot(I, P), L);
+        const double2 fb = ld_frag(tiles, slot(I, P), L);
 #pragma unroll
         for (int J = 0; J <= P; ++J) {
-          const double* q = tiles + slot(P, J) * TILE;
-          dmma(s0[J], s1[J], fa.x, q[L.tr0]); dmma(s0[J], s1[J], fa.y, q[L.tr1]);
+          const double2 fa = (J == P) ? ld_frag_t(tiles, slot(P, P), L) : ld_frag(tiles, slot(P, J), L);
+          dmma(s0[J], s1[J], fa.x, fb.x); dmma(s0[J], s1[J], fa.y, fb.y);
         }
       }
-      __syncwarp();
-#pragma unroll
-      for (int J = 0; J < I; ++J) { double* p = tiles + slot(I, J) * TILE; p[L.st0] = s0[J]; p[L.st1] = s1[J]; }
-      __syncwarp();
       const double2 ft = ld_frag(tiles, slot(I, I), L);
 #pragma unroll
       for (int J = 0; J < I; ++J) {
-        const double* q = tiles + slot(I, J) * TILE;
-        const double b0 = q[L.tr0], b1 = q[L.tr1];
-        s0[J] = 0.0; s1[J] = 0.0;
-        double e0 = 0.0, e1 = 0.0;
-        dmma(s0[J], s1[J], ft.x, b0); dmma(e0, e1, ft.y, b1);
-        s0[J] += e0; s1[J] += e1;
+        double r0 = 0.0, r1 = 0.0, e0 = 0.0, e1 = 0.0;
+        dmma(r0, r1, s0[J], ft.x); dmma(e0, e1, s1[J], ft.y);
+        s0[J] = -(r0 + e0); s1[J] = -(r1 + e1);
       }
-      __syncwarp();
 #pragma unroll
-      for (int J = 0; J < I; ++J) { double* p = tiles + slot(I, J) * TILE; p[L.st0] = -s0[J]; p[L.st1] = -s1[J]; }
+      for (int J = 0; J < I; ++J) st_frag(tiles, slot(I, J), L, s0[J], s1[J]);
       __syncwarp();
     }
+    // conversion: slot (I,J) <- its transpose = L^-1[I][J], row by row (reads cross lanes, writes stay in the lane's unit)
+#pragma unroll
+    for (int I = 1; I < NB; ++I) {
+      double2 v[NB];
+#pragma unroll
+      for (int J = 0; J < I; ++J) v[J] = ld_frag_t(tiles, slot(I, J), L);
+      __syncwarp();
+#pragma unroll
+      for (int J = 0; J < I; ++J) st_frag(tiles, slot(I, J), L, v[J].x, v[J].y);
+    }
+    __syncwarp();
 
     // ---------------- z = L^-1 r (and L^-1 1), alpha = L^-T z, d = colnorm^2(L^-1), u = L^-T L^-1 1
 #pragma unroll
@@ -411,7 +427,8 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
 #pragma unroll
       for (int J = 0; J <= I; ++J) {
         const double2 f = ld_frag(tiles, slot(I, J), L);
-        p = fma(f.x, vr[8 * J + L.t], p); p2 = fma(f.y, vr[8 * J + 4 + L.t], p2);
+        const double2 rv = ld_vec2(vr, 8 * J + 2 * L.t);
+        p = fma(f.x, rv.x, p); p2 = fma(f.y, rv.y, p2);
         if (TASK == TASK_LOO) { p1 += f.x; p1 += f.y; }
       }
       p = red_t(p + p2);
@@ -435,12 +452,12 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         }
       }
       pa0 = red_g(pa0); pa1 = red_g(pa1);
-      if (L.g == 0) { va[8 * J + L.t] = pa0; va[8 * J + 4 + L.t] = pa1; }
+      if (L.g == 0) { va[8 * J + 2 * L.t] = pa0; va[8 * J + 2 * L.t + 1] = pa1; }
       if (TASK == TASK_LOO) {
         pd0 = red_g(pd0); pd1 = red_g(pd1); pu0 = red_g(pu0); pu1 = red_g(pu1);
         if (L.g == 0) {
-          vd[8 * J + L.t] = pd0; vd[8 * J + 4 + L.t] = pd1;
-          vu[8 * J + L.t] = pu0; vu[8 * J + 4 + L.t] = pu1;
+          vd[8 * J + 2 * L.t] = pd0; vd[8 * J + 2 * L.t + 1] = pd1;
+          vu[8 * J + 2 * L.t] = pu0; vu[8 * J + 2 * L.t + 1] = pu1;
         }
       }
     }
@@ -448,6 +465,17 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     if (lane == 0 && part == 0) a.info[b] = bad;
     }   // !PF
 
+    if (FUSED && a.ll && part == 0) {                    // the likelihood from the same factorisation (z, pivots)
+      double quad = 0.0;
+#pragma unroll
+      for (int i0 = 0; i0 < LD; i0 += 32) { const int i = i0 + lane; if (i < LD) quad = fma(vz[i], vz[i], quad); }
+      quad = red_g(red_t(quad));
+      if (lane == 0) {
+        const double logdet = log(lp_m) + (double)lp_e * LN2;
+        a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+      }
+      __syncwarp();                                      // z is read before the anchors of the grid phase overwrite it
+    }
     if (TASK == TASK_FACTOR) {
       if (a.ll) {                                        // the likelihood comes for free: z and the pivots are here
         double quad = 0.0;
@@ -463,7 +491,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       double* dst = a.fws + b * a.fws_stride;
 #pragma unroll 4
       for (int q = 0; q < NT; ++q)
-        reinterpret_cast<double2*>(dst + q * TILE)[lane] = *reinterpret_cast<const double2*>(tiles + q * TILE + L.fr);
+        reinterpret_cast<double2*>(dst + q * TILE)[lane] = reinterpret_cast<const double2*>(tiles + q * TILE)[lane];
 #pragma unroll
       for (int i0 = 0; i0 < LD; i0 += 32) { const int i = i0 + lane; if (i < LD) dst[NT * TILE + i] = va[i]; }
       continue;
@@ -498,7 +526,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       continue;
     }
 
-    if (TASK == TASK_PREDICT || PF) {
+    if (FUSED || PF) {
       // ---------------- two blocks of 8 grid points per pass
       const int64_t g0 = a.goff ? a.goff[b] : 0;
       const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
@@ -551,9 +579,10 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           const bool b1 = L.g & 1, b2 = L.g & 2, b4 = L.g & 4;
 #pragma unroll
           for (int P = 0; P < NB; ++P) {
-            const int c0 = 8 * P + L.t, c1 = c0 + 4;
+            const int c0 = 8 * P + 2 * L.t, c1 = c0 + 1;   // this lane's two k-values of block P (see the layout note)
             const double2 A0 = anch[c0], A1 = anch[c1];
-            const double al0 = va[c0], al1 = va[c1];
+            const double2 al = ld_vec2(va, c0);
+            const double al0 = al.x, al1 = al.y;
             // R^g by squaring (g is fixed per lane: predicated multiplies), R^(g+8) = R^g R^8
             const double r02 = A0.y * A0.y, r04 = r02 * r02, r08 = r04 * r04;
             const double r12 = A1.y * A1.y, r14 = r12 * r12, r18 = r14 * r14;
@@ -570,10 +599,12 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         } else {
 #pragma unroll
         for (int P = 0; P < NB; ++P) {
-          const int c0 = 8 * P + L.t, c1 = c0 + 4;
-          const double x0 = px[c0], x1 = px[c1];
-          const double y0c = DIM == 2 ? px[LD + c0] : 0.0, y1c = DIM == 2 ? px[LD + c1] : 0.0;
-          const double al0 = va[c0], al1 = va[c1];
+          const int c0 = 8 * P + 2 * L.t, c1 = c0 + 1;
+          const double2 xx = ld_vec2(px, c0), al = ld_vec2(va, c0);
+          const double x0 = xx.x, x1 = xx.y;
+          double y0c = 0.0, y1c = 0.0;
+          if (DIM == 2) { const double2 yy = ld_vec2(px + LD, c0); y0c = yy.x; y1c = yy.y; }
+          const double al0 = al.x, al1 = al.y;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             double e0 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x0, y0c));
@@ -735,11 +766,10 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         constexpr int i = decltype(ic)::value;
         s0[i] = k0[i] - (s0[i] + u0[i]); s1[i] = k1[i] - (s1[i] + u1[i]);
       });
+      double t0, t1;                                    // T_J = L_JJ^-1 stays in registers: both its uses take it from there
       {
-        double t0, t1, piv; int badk;
+        double piv; int badk;
         diag_factor(s0[0], s1[0], L, t0, t1, piv, badk);
-        double* p = tiles + kPhys[NB - 1][J][J] * TILE;
-        p[L.st0] = t0; p[L.st1] = t1;
         lp_m *= piv;
         const int hi = __double2hiint(lp_m);
         const int e = ((hi >> 20) & 0x7ff) - 1023;
@@ -747,25 +777,17 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         lp_m = __hiloint2double(hi - (e << 20), __double2loint(lp_m));
         if (badk && bad == 0) bad = 8 * J + badk;
       }
-      static_for<1, NTJ>([&](auto ic) {                 // park C[I][J] to re-read it as an A fragment
-        constexpr int i = decltype(ic)::value;
-        double* p = tiles + kPhys[NB - 1][J + i][J] * TILE;
-        p[L.st0] = s0[i]; p[L.st1] = s1[i];
-      });
-      __syncwarp();
-      const double2 ft = ld_frag(tiles, kPhys[NB - 1][J][J], L);
       if constexpr (NTJ > 1) {
-        static_for<1, NTJ>([&](auto ic) {               // L[I][J] = C[I][J] T_J^T
+        static_for<1, NTJ>([&](auto ic) {               // L[I][J] = C[I][J] T_J^T, operands = accumulators (layout note)
           constexpr int i = decltype(ic)::value;
-          const double2 fc = ld_frag(tiles, kPhys[NB - 1][J + i][J], L);
+          const double c0 = s0[i], c1 = s1[i];
           s0[i] = 0.0; s1[i] = 0.0; u0[i] = 0.0; u1[i] = 0.0;
-          dmma(s0[i], s1[i], fc.x, ft.x); dmma(u0[i], u1[i], fc.y, ft.y);
+          dmma(s0[i], s1[i], c0, t0); dmma(u0[i], u1[i], c1, t1);
         });
-        __syncwarp();
         static_for<1, NTJ>([&](auto ic) {
           constexpr int i = decltype(ic)::value;
-          double* p = tiles + kPhys[NB - 1][J + i][J] * TILE;
-          p[L.st0] = s0[i] + u0[i]; p[L.st1] = s1[i] + u1[i];
+          constexpr int ps = kPhys[NB - 1][J + i][J];
+          st_frag(tiles, ps, L, s0[i] + u0[i], s1[i] + u1[i]);
         });
       }
       // z_J = T_J (r_J - sum_{P<J} L[J][P] z_P); afterwards row J is dead and its slots are reused
@@ -773,10 +795,11 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       static_for<0, J>([&](auto Pc) {
         constexpr int P = decltype(Pc)::value;
         const double2 f = ld_frag(tiles, kPhys[NB - 1][J][P], L);
-        pz = fma(f.x, vr[8 * P + L.t], pz); pz2 = fma(f.y, vr[8 * P + 4 + L.t], pz2);
+        const double2 rv = ld_vec2(vr, 8 * P + 2 * L.t);
+        pz = fma(f.x, rv.x, pz); pz2 = fma(f.y, rv.y, pz2);
       });
       const double wv = vr[8 * J + L.g] - red_t(pz + pz2);
-      double q = ft.x * __shfl_sync(FULL, wv, L.t * 4) + ft.y * __shfl_sync(FULL, wv, (4 + L.t) * 4);
+      double q = t0 * __shfl_sync(FULL, wv, L.t * 8) + t1 * __shfl_sync(FULL, wv, L.t * 8 + 4);
       q = red_t(q);
       if (L.t == 0) { vr[8 * J + L.g] = q; quad = fma(q, q, quad); }
       __syncwarp();
@@ -837,7 +860,7 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
   }
-  const int64_t n_work = a.n_obj * ((TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU) ? a.split : 1);
+  const int64_t n_work = a.n_obj * ((TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU || TASK == TASK_PREDICT_U) ? a.split : 1);
   static int cap = -1;                                    // experiment knob: CGP_GP64_PER_SM=<blocks per SM>
   if (cap < 0) { const char* e = getenv("CGP_GP64_PER_SM"); cap = e ? atoi(e) : 0; }
   int64_t grid = (int64_t)sm_count * ((cap > 0 && cap < per_sm) ? cap : per_sm);
@@ -870,7 +893,7 @@ int launch64_nb(int nb, const SmallArgs& a, cudaStream_t stream) {
 // One (DIM, TASK) pair per translation unit (build.py compiles this file eleven times with
 // -DCGP64_DIM / -DCGP64_TASK) so the 88 static instantiations build in parallel.
 #ifndef CGP64_DIM
-#error "compile with -DCGP64_DIM=1|2 -DCGP64_TASK=0|1|2|4|5|6"
+#error "compile with -DCGP64_DIM=1|2 -DCGP64_TASK=0|1|2|4|5|6|7"
 #endif
 #define CGP64_CAT2(a, b, c, d) a##b##c##d
 #define CGP64_CAT(a, b, c, d) CGP64_CAT2(a, b, c, d)

@@ -173,6 +173,17 @@ int cgp_predict_batched_host(int64_t n_obj, const int64_t* off, int dim,
                              const double* xnew, const int64_t* goff, int64_t m_shared,
                              const double* new_y0, double* mean, double* var, int* info);
 
+/* ---- one pass of the hot path: compute_log_likelihood (cosmogp/Gaussian_process.py:191-213) AND get_prediction
+ *      (:270-361) at the same hyperparameters from ONE factorisation per object -- what a fit's final evaluation
+ *      followed by the interpolation amounts to.  Arguments as cgp_predict_batched_dev plus ll_obj[n_obj]
+ *      (per-object log-likelihood, NaN where info != 0).  Objects of <= 64 points: a single kernel, the covariance
+ *      and its factor never leave shared memory. */
+int cgp_step_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                         const double* x, const double* y, const double* y0, const double* y_err,
+                         const double* hyp, double nugget, double floor, unsigned flags,
+                         const double* xnew, const int64_t* goff, int64_t m_shared,
+                         const double* new_y0, double* ll_obj, double* mean, double* var, int* info, void* stream);
+
 /* ---- factor once, predict on any number of grids (objects of <= 64 points): the two halves of
  *      cgp_predict_batched_dev as separate calls.  ws holds, per object, inv(L) as 8x8 tiles in DMMA
  *      fragment order followed by alpha = K^-1 (y - y0): cgp_factor_ws_doubles(max_n) doubles each.
