@@ -36,6 +36,7 @@ SIGNATURES = {
     "cgp_fp64_peak": (_int, [_int, C.POINTER(_dbl)]),
     "cgp_launch_count": (_i64, []),
     "cgp_ll_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_ptr, _ptr, _ptr]),
+    "cgp_ll_total_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_ptr, _ptr, _ptr, _ptr, _ptr]),
     "cgp_ll_batched_host": (_int, _BATCH + [_ptr] * 4 + _HYP + [_ptr, _ptr, C.POINTER(_dbl)]),
     "cgp_ll_objhyp_dev": (_int, _BATCH_DEV + [_ptr] * 4 + [_ptr, _ptr, _dbl, _dbl, _u32, _ptr, _i64, _ptr, _ptr, _ptr]),
     "cgp_streamer_create": (_int, [_i64, _int, _i64, _int, _int, C.POINTER(_ptr)]),
@@ -59,6 +60,19 @@ SIGNATURES = {
     "cgp_loo_batched_dev": (_int, _BATCH_DEV + [_ptr] * 4 + _HYP + [_int] + [_ptr] * 4 + [_ptr, _ptr]),
     "cgp_loo_batched_host": (_int, _BATCH + [_ptr] * 4 + _HYP + [_int] + [_ptr] * 4 + [_ptr]),
     "cgp_matrices_batched_dev": (_int, _BATCH_DEV + [_ptr] * 2 + _HYP + [_ptr, _ptr, _ptr, _ptr, _ptr]),
+    "cgp_set_nccl_library": (_int, [C.c_char_p]),
+    "cgp_shard_ranges": (_int, [_i64, _ptr, _int, _ptr]),
+    "cgp_ctx_create": (_int, [_int, _ptr, C.POINTER(_ptr)]),
+    "cgp_ctx_destroy": (None, [_ptr]),
+    "cgp_ctx_info": (_int, [_ptr, C.POINTER(_int), C.POINTER(_int)]),
+    "cgp_ctx_gather_f64": (_int, [_ptr, _ptr, _ptr, _ptr, _int]),
+    "cgp_ctx_allreduce_sum_f64": (_int, [_ptr, _ptr, _i64]),
+    "cgp_ctx_batch_create": (_int, [_ptr, _i64, _ptr, _int, _ptr, _ptr, _ptr, _ptr, C.POINTER(_ptr)]),
+    "cgp_ctx_batch_destroy": (None, [_ptr]),
+    "cgp_ctx_batch_ranges": (_int, [_ptr, _ptr]),
+    "cgp_ctx_batch_ll": (_int, [_ptr, _ptr, _dbl, _dbl, _u32, C.POINTER(_dbl), _ptr, _ptr]),
+    "cgp_ctx_batch_predict": (_int, [_ptr, _ptr, _dbl, _dbl, _u32, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int]),
+    "cgp_ctx_batch_loo": (_int, [_ptr, _ptr, _dbl, _dbl, _u32, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _int]),
     "cgp_pad128": (_i64, [_i64]),
     "cgp_cov_matrix_dev": (_int, [_int, _ptr, _i64, _ptr, _i64, _ptr] + _HYP + [_ptr, _i64, _i64, _i64, _ptr]),
     "cgp_potrf_dev": (_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr]),

@@ -59,6 +59,17 @@ class RaggedView(object):
     def __iter__(self):
         return (self[i] for i in range(len(self)))
 
+    def __array__(self, dtype=None, copy=None):
+        """equal-length objects -> the (B, n) array (a view of the flat data); ragged -> an object array of views"""
+        sizes = np.diff(self.off)
+        if len(sizes) and np.all(sizes == sizes[0]) and self.off[0] == 0:
+            out = self.flat[:self.off[-1]].reshape(len(sizes), int(sizes[0]), *self.flat.shape[1:])
+            return out if dtype is None else out.astype(dtype)
+        out = np.empty(len(self), dtype=object)
+        for i in range(len(self)):
+            out[i] = self[i]
+        return out
+
     def extended(self, flat, off):
         """view over this view's data followed by another batch (compute_pull appends across calls)."""
         off = np.asarray(off, dtype=np.int64)
@@ -118,13 +129,18 @@ class DeviceBatch:
         assert len(h) == need, "expected %d hyperparameters, got %d" % (need, len(h))
         return h
 
-    def _down(self, t):
-        """Device -> pinned host (torch's caching host allocator recycles the blocks)."""
+    def _down(self, t, sync=True):
+        """Device -> pinned host (torch's caching host allocator recycles the blocks).  sync=False only enqueues the
+        copy: the caller batches several downloads and calls _sync() once before touching the arrays."""
         self.d2h_bytes += t.numel() * t.element_size()
         out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         out.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
         return out.numpy()
+
+    def _sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
 
     # ---- the hot path
     def ll_dev(self, hyp, nugget=0.0, floor=0.0, flags=0):
@@ -138,6 +154,41 @@ class DeviceBatch:
                                                self._stream())
         _lib.check(rc, "cgp_ll_batched_dev")
         return ll[:self.n_obj], self._info[:self.n_obj]
+
+    def log_likelihood_total(self, hyp, nugget=0.0, floor=0.0, flags=0):
+        """One likelihood evaluation as the optimiser needs it (cgp_ll_total_dev): the per-object values and the
+        `info` flags stay on the device (`ll_host()` / `info_host()` fetch them), the sum over objects is reduced there
+        in a fixed order and 16 bytes come back.  -> (sum, number of non-positive-definite objects).
+        No allocation, one native call and one stream synchronisation per evaluation."""
+        c = getattr(self, "_tot", None)
+        if c is None:
+            ll = torch.empty(max(self.n_obj, 1), dtype=torch.float64, device=self.device)
+            tot_d = torch.zeros(2, dtype=torch.float64, device=self.device)
+            tot_h = torch.zeros(2, dtype=torch.float64, pin_memory=True)
+            nh = 2 if self.dim == 1 else 4
+            c = self._tot = {"ll": ll, "tot_d": tot_d, "tot_h": tot_h, "tot_np": tot_h.numpy(), "hyp": np.zeros(nh),
+                             "fn": _lib.lib().cgp_ll_total_dev, "dev_index": self.device.index,
+                             "args": (self.n_obj, self._p(self.off), self.max_n, self.dim, self._p(self.x), self._p(self.y),
+                                      self._p(self.y0), self._p(self.y_err)),
+                             "out": (ll.data_ptr(), self._info.data_ptr(), tot_d.data_ptr(), tot_h.data_ptr())}
+            c["hyp_ptr"] = c["hyp"].ctypes.data
+        h = c["hyp"]
+        h[:] = hyp                                           # raises on a wrong number of hyperparameters
+        if torch.cuda.current_device() != c["dev_index"]:
+            with torch.cuda.device(self.device):
+                rc = c["fn"](*c["args"], c["hyp_ptr"], float(nugget), float(floor), int(flags), *c["out"], self._stream())
+        else:
+            rc = c["fn"](*c["args"], c["hyp_ptr"], float(nugget), float(floor), int(flags), *c["out"], self._stream())
+        _lib.check(rc, "cgp_ll_total_dev")
+        self.d2h_bytes += 16
+        return float(c["tot_np"][0]), int(rc)
+
+    def ll_host(self):
+        """per-object log-likelihoods of the latest log_likelihood_total() call, brought to the host"""
+        return self._down(self._tot["ll"][:self.n_obj])
+
+    def info_host(self):
+        return self._down(self._info[:self.n_obj])
 
     def log_likelihood(self, hyp, nugget=0.0, floor=0.0, flags=0):
         """-> (sum over objects in index order, per-object LL, info), all host numpy."""
@@ -326,9 +377,10 @@ class DeviceBatch:
         if goff is None and self.dim == 1:
             flags = int(flags) | _lib.CGP_GRID_UNIFORM          # a hint; the library checks the grid and the length scale
         mean, var, info = self.predict_dev(hyp, nugget, g, go, ny0, want_var, floor, flags)
-        mean_h = self._down(mean)
-        var_h = self._down(var) if want_var else None
-        info_h = self._down(info)
+        mean_h = self._down(mean, sync=False)                # three copies in flight, one synchronisation
+        var_h = self._down(var, sync=False) if want_var else None
+        info_h = self._down(info, sync=False)
+        self._sync()
         if goff is None:
             m = int(g.shape[0])
             mean_h = mean_h.reshape(self.n_obj, m)

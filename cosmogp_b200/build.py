@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcosmogp_b200.so")
-SOURCES = ["cgp_api.cu", "cgp_small.cu", "cgp_large.cu", "cgp_fit.cu", "cgp_stream.cu"]
+SOURCES = ["cgp_api.cu", "cgp_small.cu", "cgp_large.cu", "cgp_fit.cu", "cgp_stream.cu", "cgp_ctx.cu"]
 HEADERS = [os.path.join(CSRC, "cgp_internal.h"), os.path.join(CSRC, "cgp_math.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "cosmogp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -181,6 +181,24 @@ int cgp_ll_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
   return run_small(TASK_LL, dim, max_n, a, st, "cgp_ll_batched_dev");
 }
 
+int cgp_ll_total_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                     const double* x, const double* y, const double* y0, const double* y_err,
+                     const double* hyp, double nugget, double floor, unsigned flags,
+                     double* ll_obj, int* info, double* total_dev, double* total_host, void* stream) {
+  if (n_obj < 0 || !total_dev) return fail(CGP_ERR_ARG, "cgp_ll_total_dev: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = cgp_ll_batched_dev(n_obj, off, max_n, dim, x, y, y0, y_err, hyp, nugget, floor, flags, ll_obj, info, stream);
+  if (rc) return rc;
+  keep_pool_memory();
+  int e = large_ll_total(ll_obj, info, n_obj, total_dev, st);
+  if (e) return cuda_fail(e, "cgp_ll_total_dev (reduction)");
+  if (!total_host) return 0;
+  cudaError_t ce = cudaMemcpyAsync(total_host, total_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) return cuda_fail((int)ce, "cgp_ll_total_dev (read back)");
+  return total_host[1] > 2147483647.0 ? 2147483647 : (int)total_host[1];
+}
+
 int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
                         const double* x, const double* y, const double* y0, const double* y_err,
                         const double* hyp, double nugget, double floor, unsigned flags,
@@ -303,16 +321,18 @@ static int predict_impl(int64_t n_obj, const int64_t* off, int max_n, int dim,
     if ((rc = run_small(TASK_LL, dim, max_n, l, st, "cgp_step_batched_dev (likelihood)"))) return rc;
     a.ll = nullptr;
   }
-  // Many small objects with variances.  Default: ONE kernel per object batch (TASK_PREDICT / TASK_PREDICT_U): each
-  // warp factorises its object and runs the grid phase from the same shared-memory tiles, so the factor never
-  // travels through HBM, and the latency-bound factorisation of one warp hides behind the DMMA-dense grid phase
-  // of its neighbours.  CGP_PREDICT_SPLIT=1 selects the two-kernel form instead (FACTOR spills L^-1 and alpha to
-  // a workspace, PREDICT_F stages them back by TMA): what factor-once / predict-many callers use.
+  // Many small objects with variances: two kernels by default.  FACTOR (latency-bound factorisation, L^-1 and alpha
+  // spilled to a workspace) then PREDICT_F / PREDICT_FU (every warp in the DMMA-dense grid phase, factor staged by
+  // TMA).  The one-pass kernel (TASK_PREDICT_U: factorise and predict from the same shared-memory tiles, nothing
+  // spilled; CGP_PREDICT_FUSED=1) moves 11x less HBM traffic but is slower on B200 (4.4 vs 4.1 ms at C2, ncu r02c:
+  // 20 % of its stalls are instruction fetch -- factorisation + grid code exceed the 32 KB L1.5 instruction cache --
+  // and with 11 one-warp CTAs per SM a single warp in the grid phase cannot keep the FP64 pipe busy while its
+  // neighbours factorise).  Small batches (< 2048 objects) always take the one-pass kernel.
   static int use_split = -1;
-  if (use_split < 0) { const char* e = getenv("CGP_PREDICT_SPLIT"); use_split = (e && atoi(e)) ? 1 : 0; }
+  if (use_split < 0) { const char* e = getenv("CGP_PREDICT_FUSED"); use_split = (e && atoi(e)) ? 0 : 1; }
   if (!use_split && var && max_n <= 64 && n_obj >= 2048 && split == 1 && (flags & CGP_GRID_UNIFORM) && dim == 1 && !goff &&
       !hyp_obj && m_shared >= 2 && uniform_grid_ok_dev(xnew, m_shared, hyp, st))
-    return run_small(TASK_PREDICT_U, dim, max_n, a, st, "cgp_predict_batched_dev (fused, uniform grid)");
+    return run_small(TASK_PREDICT_U, dim, max_n, a, st, "cgp_predict_batched_dev (one pass, uniform grid)");
   if (use_split && var && max_n <= 64 && n_obj >= 2048 && split == 1) {
     const int nb = max_n < 1 ? 1 : (max_n + 7) / 8;
     const int64_t stride = factor_ws_doubles(nb);

@@ -114,6 +114,7 @@ int large_row_var(const double* v, int64_t ldv, int64_t n_pad, int64_t rows, dou
 int large_spline_mean(const double* t, const double* c, int nt, const double* x, int64_t n_pts, const int64_t* off,
                       int64_t n_obj, const double* diff, double* out, cudaStream_t st);
 int large_moments(const double* v, int64_t n, double center, double* out2, cudaStream_t st);
+int large_ll_total(const double* ll, const int* info, int64_t n, double* out2, cudaStream_t st);
 int large_dot_sq(const double* v, int64_t n, double* out, cudaStream_t st);
 int large_residual(const double* y, const double* y0, int64_t n, int64_t n_pad, double* r, cudaStream_t st);
 

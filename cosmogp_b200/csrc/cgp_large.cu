@@ -437,11 +437,13 @@ __global__ void residual_kernel(const double* y, const double* y0, int64_t n, in
 // =========================================================================================
 int launch_gemm_nt(const GemmArgs& g, cudaStream_t stream) {
   if (g.m % 128 || g.n % BN || g.k % BK || g.m <= 0 || g.n <= 0 || g.k <= 0) return (int)cudaErrorInvalidValue;
-  static bool init = false;
-  if (!init) {
+  static bool init[16] = {false};                         // function attributes are per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return (int)cudaErrorInvalidDevice;
+  if (!init[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return (int)e;
-    init = true;
+    init[dev] = true;
   }
   const int64_t tm = g.m / BM, tn = g.n / BN;
   const int64_t t128 = g.m / 128;
@@ -579,6 +581,10 @@ int large_potrf(double* a, int64_t n_pad, int64_t ld, double* logdet_out, int* i
     }
     cudaStreamWaitEvent(st, ev_panel, 0);
   }
+  if (rc) {                                            // error exit: the side stream may still be using the scratch
+    cudaEventRecord(ev_panel, side);
+    cudaStreamWaitEvent(st, ev_panel, 0);
+  }
   potrf_finish_kernel<<<1, 32, 0, st>>>(logdet_blocks, info_blocks, nblk, logdet_out, info_out);
   count_launch();
   cudaFreeAsync(scratch, st);
@@ -675,6 +681,48 @@ int large_moments(const double* v, int64_t n, double center, double* out2, cudaS
   if (ce != cudaSuccess) return (int)ce;
   moments_partial_kernel<<<nblk, 256, 0, st>>>(v, n, center, partial);
   moments_final_kernel<<<1, 256, 0, st>>>(partial, nblk, out2);
+  count_launch(2);
+  cudaFreeAsync(partial, st);
+  return (int)cudaGetLastError();
+}
+// sum of the per-object log-likelihoods in a FIXED order (block b sums its contiguous segment with 256 strided
+// lanes + a tree, one thread adds the block partials in index order) and the number of objects with info != 0.
+__global__ void __launch_bounds__(256) ll_total_partial_kernel(const double* __restrict__ ll, const int* __restrict__ info,
+                                                               int64_t n, double* __restrict__ partial) {
+  __shared__ double s1[8], s2[8];
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+  double a = 0.0, b = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) { a += ll[i]; b += info[i] != 0 ? 1.0 : 0.0; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int w = 0; w < 8; ++w) { t1 += s1[w]; t2 += s2[w]; }
+    if (gridDim.x == 1) { partial[0] = t1; partial[1] = t2; }           // `partial` is the output itself
+    else { partial[2 * blockIdx.x] = t1; partial[2 * blockIdx.x + 1] = t2; }
+  }
+}
+__global__ void ll_total_final_kernel(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int i = 0; i < nblk; ++i) { t1 += partial[2 * i]; t2 += partial[2 * i + 1]; }
+    out[0] = t1; out[1] = t2;
+  }
+}
+int large_ll_total(const double* ll, const int* info, int64_t n, double* out2, cudaStream_t st) {
+  if (n <= 16384) {                                      // one block: one launch
+    ll_total_partial_kernel<<<1, 256, 0, st>>>(ll, info, n, out2); count_launch();
+    return (int)cudaGetLastError();
+  }
+  int nblk = (int)((n + 8191) / 8192); if (nblk > 256) nblk = 256;
+  double* partial = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&partial, sizeof(double) * 2 * nblk, st);
+  if (e != cudaSuccess) return (int)e;
+  ll_total_partial_kernel<<<nblk, 256, 0, st>>>(ll, info, n, partial);
+  ll_total_final_kernel<<<1, 32, 0, st>>>(partial, nblk, out2);
   count_launch(2);
   cudaFreeAsync(partial, st);
   return (int)cudaGetLastError();

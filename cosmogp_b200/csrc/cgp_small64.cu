@@ -818,15 +818,19 @@ template <int DIM, int NB>
 int launch64_ll(const SmallArgs& a, cudaStream_t stream) {
   auto kern = gp64_ll_kernel<DIM, NB>;
   const size_t smem = ((size_t)kPhysSlots[NB - 1] * TILE + (size_t)(DIM + 2) * 8 * NB) * sizeof(double);
-  static int sm_count = 0, per_sm = 0;
-  if (!sm_count) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  static int sm_counts[16] = {0}, per_sms[16] = {0};   // per device of this process (function attributes are per device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return (int)cudaErrorInvalidDevice;
+  int& sm_count = sm_counts[dev]; int& per_sm = per_sms[dev];
+  if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (!per_sm) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem);
     if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
-    if (per_sm > 16) per_sm = 16;                        // 4 warps per sub-partition
+    if (occ < 1) return (int)cudaErrorInvalidConfiguration;
+    per_sm = occ > 16 ? 16 : occ;                        // 4 warps per sub-partition
   }
   static int cap = -1;
   if (cap < 0) { const char* e = getenv("CGP_GP64_PER_SM"); cap = e ? atoi(e) : 0; }
@@ -847,18 +851,19 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
   if (TASK == TASK_LL && compact) return launch64_ll<DIM, NB>(a, stream);
   auto kern = gp64_kernel<DIM, TASK, NB>;
   const size_t smem = ((size_t)(NB * (NB + 1) / 2) * TILE + (size_t)(DIM + 1 + n_vec64(TASK)) * 8 * NB) * sizeof(double);
-  static int sm_count = 0;
-  static int per_sm = 0;
-  if (!sm_count) {
-    int dev; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static int sm_counts[16] = {0}, per_sms[16] = {0};   // per device of this process
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return (int)cudaErrorInvalidDevice;
+  int& sm_count = sm_counts[dev]; int& per_sm = per_sms[dev];
+  if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (!per_sm) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem);
     if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) return (int)cudaErrorInvalidConfiguration;
+    if (occ < 1) return (int)cudaErrorInvalidConfiguration;
+    per_sm = occ;
   }
   const int64_t n_work = a.n_obj * ((TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU || TASK == TASK_PREDICT_U) ? a.split : 1);
   static int cap = -1;                                    // experiment knob: CGP_GP64_PER_SM=<blocks per SM>

@@ -31,6 +31,10 @@ from .batch import DeviceBatch, RaggedView, pack_csr
 from .kernel import init_rbf, rbf_kernel_1d, rbf_kernel_2d
 
 
+_DEVICE = object()                       # marker: the per-object likelihoods of the latest evaluation are still on the device
+_NO_BAD = np.zeros(0, dtype=np.int32)
+
+
 class _LazyMatrices(object):
     """list-like of per-object matrices computed on the device on first access."""
 
@@ -78,7 +82,10 @@ class Gaussian_process:
 
     def __init__(self, y, Time, kernel='RBF1D',
                  y_err=None, diff=None, Mean_Y=None,
-                 Time_mean=None, substract_mean=False):
+                 Time_mean=None, substract_mean=False, devices=None):
+        """Arguments of cosmogp/Gaussian_process.py:82-88, plus `devices` (None: the current GPU; 'all', an int or a
+        list of device ids: the objects are sharded over those GPUs of the box inside this process -- see
+        cosmogp_b200.multi.ShardedBatch; likelihood, joint fit and shared-grid predictions are available there)."""
         kernel_choice = ['RBF1D', 'RBF2D']
         assert kernel in kernel_choice, '%s is not in implemented kernel' % (kernel)
 
@@ -119,6 +126,9 @@ class Gaussian_process:
             self.y0 = np.zeros(self.N_sn)
 
         self.as_the_same_time = True
+        self._ll_per_object = None
+        self._devices = devices
+        self.gather_over_nvlink = False     # multi-GPU outputs: False = every GPU's own PCIe link, True = NCCL gather on GPU 0 first
         self._batch = None
         self._dist = False              # True for objects made by `sharded()`: likelihoods are all-reduced
 
@@ -141,8 +151,9 @@ class Gaussian_process:
         obj._dist, obj.local_range, obj.N_total, obj._all_sizes = True, (a, b), len(y), sizes
         return obj
 
-    def gather(self, per_object_arrays):
-        """All ranks' per-object arrays (e.g. `Prediction`) concatenated in object order, on every rank."""
+    def gather(self, per_object_arrays, root=None):
+        """All ranks' per-object arrays (e.g. `Prediction`) concatenated in object order: on every rank (root=None,
+        an all-gather) or on rank `root` only (the final gather: each rank sends its slice once; None elsewhere)."""
         from . import sharding
         flat = np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in per_object_arrays]) if len(per_object_arrays) else np.zeros(0)
         per = [len(np.asarray(v).ravel()) for v in per_object_arrays]
@@ -154,6 +165,9 @@ class Gaussian_process:
         assert width and all(p == width for p in per), "gather() needs a prediction on a shared grid"
         ranges = sharding.balanced_ranges(self._all_sizes, dist.get_world_size())
         counts = [(r[1] - r[0]) * width for r in ranges]
+        if root is not None:
+            allflat = sharding.gather_to_root(flat, counts, root=root, device=self._device)
+            return None if allflat is None else list(allflat.reshape(-1, width))
         allflat = sharding.gather_ragged(flat, counts, device=self._device)
         return list(allflat.reshape(-1, width)) if width else []
 
@@ -161,8 +175,13 @@ class Gaussian_process:
     @property
     def batch(self):
         if self._batch is None:
-            self._batch = DeviceBatch(self._x_flat, self._y_flat, self._off, y0=self._y0_flat,
-                                      y_err=self._ye_flat, dim=self._dim)
+            if self._devices is not None:
+                from .multi import ShardedBatch
+                self._batch = ShardedBatch(self._x_flat, self._y_flat, self._off, y0=self._y0_flat,
+                                           y_err=self._ye_flat, dim=self._dim, devices=self._devices)
+            else:
+                self._batch = DeviceBatch(self._x_flat, self._y_flat, self._off, y0=self._y0_flat,
+                                          y_err=self._ye_flat, dim=self._dim)
         return self._batch
 
     @property
@@ -216,7 +235,12 @@ class Gaussian_process:
                     info[i] = 1
             total = None
         else:
-            total, per_object, info = self.batch.log_likelihood(hyperparameter, Nugget, flags=self.flags)
+            # the sum over objects is reduced on the device: 16 bytes come back per evaluation, the per-object
+            # values stay there until `log_likelihood_per_object` is read
+            total, n_bad = self.batch.log_likelihood_total(hyperparameter, Nugget, flags=self.flags)
+            per_object, info = _DEVICE, _NO_BAD
+            if n_bad:
+                per_object, info = self.batch.ll_host(), self.batch.info_host()
         if info.any() and svd_method:                       # the reference's default never raises (inv_matrix.py:4-18)
             per_object = np.array(per_object, dtype=float)
             for i in np.nonzero(info)[0]:
@@ -227,13 +251,23 @@ class Gaussian_process:
             total = float(np.add.accumulate(per_object)[-1]) if len(per_object) else 0.0
         if self._dist:
             from . import sharding
-            bad = sharding.allreduce_sum(float(np.count_nonzero(info)), device=self._device)
+            total, bad = sharding.allreduce_sums([total, float(np.count_nonzero(info))], device=self._device)
             if bad:
                 raise np.linalg.LinAlgError("%d object(s) with a covariance that is not positive definite" % int(bad))
-            total = sharding.allreduce_sum(total, device=self._device)
         self._raise_if_bad(info)
         self.log_likelihood_per_object = per_object
         self.log_likelihood = np.array([total])             # shape (1,), quirk Q5
+
+    @property
+    def log_likelihood_per_object(self):
+        """per-object log-likelihoods of the latest evaluation (fetched from the device when first read)"""
+        if self._ll_per_object is _DEVICE:
+            self._ll_per_object = self.batch.ll_host().copy()
+        return self._ll_per_object
+
+    @log_likelihood_per_object.setter
+    def log_likelihood_per_object(self, value):
+        self._ll_per_object = value
 
     def _svd_object(self, i, hyperparameter, nugget, grid=None, new_y0=0.0, want_var=False):
         """ONE object through the host reference check (inv_matrix.svd_inverse): used only for objects whose
@@ -352,6 +386,9 @@ class Gaussian_process:
         object with its own fit (`hyperparameters_per_object`, `nugget_per_object`); COV must then
         be 'diag' or False."""
         hyp, nug = np.array(self.hyperparameters, dtype=float), float(self.nugget)
+        if self._devices is not None:
+            assert new_binning is not None and not per_object and COV in ('diag', False) and not self._is_large, \
+                "with devices=... predictions are on a shared grid with COV='diag' or False"
         if per_object:
             assert COV in ('diag', False), "per_object predictions provide the variance diagonal only"
             hyp_b, nug_b = self.hyperparameters_per_object, self.nugget_per_object
@@ -422,8 +459,9 @@ class Gaussian_process:
                 tmpl = _mean.template_on_grid(grid, self._dim, self.Mean_Y, self.Time_mean)
                 mean_template = (np.zeros(m) if tmpl is None else tmpl, self._diff_used)
                 new_y0 = _LazyMeanOnGrid(*mean_template)
+            kw = {"gather": self.gather_over_nvlink} if self._devices is not None else {}
             mean, var, info = self.batch.predict(hyp_b if per_object else hyp, nug_b if per_object else nug, grid,
-                                                 mean_template=mean_template, want_var=want_var, flags=self.flags)
+                                                 mean_template=mean_template, want_var=want_var, flags=self.flags, **kw)
             if info.any() and svd_method and not per_object:
                 for i in np.nonzero(info)[0]:
                     ny0 = (mean_template[0] + mean_template[1][i]) if has_mean else 0.0
@@ -432,8 +470,10 @@ class Gaussian_process:
                         var[i] = v
                 info = np.zeros_like(info)
             self._raise_if_bad(info)
-            self.Prediction = list(mean)
-            self.prediction_variance = list(var) if want_var else None
+            # list-like row views built in O(1) (a real list of 10^5 row arrays costs ~15 ms)
+            rows = np.arange(self.N_sn + 1, dtype=np.int64) * m
+            self.Prediction = RaggedView(mean.reshape(-1), rows)
+            self.prediction_variance = RaggedView(var.reshape(-1), rows) if want_var else None
         self.warning_pf = new_y0
         if COV is True:
             self.get_covariance_matrix()
@@ -470,8 +510,8 @@ class gaussian_process_nobject(Gaussian_process):
 
     def __init__(self, y, Time, kernel='RBF1D',
                  y_err=None, diff=None, Mean_Y=None,
-                 Time_mean=None, substract_mean=False):
+                 Time_mean=None, substract_mean=False, devices=None):
         """Run gp for n objects (:382-393)."""
         Gaussian_process.__init__(self, y, Time, kernel=kernel,
                                   y_err=y_err, diff=diff, Mean_Y=Mean_Y,
-                                  Time_mean=Time_mean, substract_mean=substract_mean)
+                                  Time_mean=Time_mean, substract_mean=substract_mean, devices=devices)

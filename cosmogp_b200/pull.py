@@ -15,10 +15,14 @@ class build_pull:
 
     def __init__(self, y, x, hyperparameters, nugget=0.,
                  y_err=None, y_mean=None, x_axis_mean=None,
-                 kernel='RBF1D'):
+                 kernel='RBF1D', devices=None, gather_over_nvlink=False):
         """Same arguments and attributes as cosmogp/pull.py:10-40.  `hyperparameters` (and `nugget`) may
         also be per-object arrays of shape (n_object, n_hyp) / (n_object,): each object is then
-        pulled with its own fit, as in the reference's per-object notebook loop."""
+        pulled with its own fit, as in the reference's per-object notebook loop.
+        devices ('all', an int or a list of device ids): the objects are sharded over those GPUs of the box inside
+        this process (cosmogp_b200.multi.ShardedBatch; shared hyperparameters); gather_over_nvlink=True collects
+        the per-object outputs on GPU 0 with NCCL before they leave the box's GPUs (False: every GPU's own PCIe link)."""
+        self._devices, self._gather = devices, bool(gather_over_nvlink)
         self.y = y
         self.x = x
         self.hyperparameters = hyperparameters
@@ -69,22 +73,44 @@ class build_pull:
             else:
                 template = template + np.repeat(np.asarray(diff, dtype=float), np.diff(off))
 
-        batch = DeviceBatch(x_flat, y_flat, off, y0=template, y_err=ye_flat, dim=dim)
-        pred, pvar, pull, resid, info = batch.loo_dev(self.hyperparameters, self.nugget, mode=mode, flags=self.flags)
-        bad = np.nonzero(batch._down(info))[0]
-        if len(bad):
-            raise np.linalg.LinAlgError("covariance of object %d is not positive definite" % int(bad[0]))
-        self._results.append({"batch": batch, "off": off, "pull": pull, "residual": resid, "prediction": pred,
-                              "prediction_variance": pvar})
+        if self._devices is not None:
+            from .multi import ShardedBatch
+            assert np.ndim(self.hyperparameters) == 1, "with devices=... the hyperparameters are shared by all objects"
+            sb = ShardedBatch(x_flat, y_flat, off, y0=template, y_err=ye_flat, dim=dim, devices=self._devices)
+            pred, pvar, pull, resid, info, mom = sb.loo(self.hyperparameters, self.nugget, mode=mode, flags=self.flags,
+                                                        gather=self._gather)
+            self.shard_ranges = sb.ranges
+            sb.close()
+            bad = np.nonzero(info)[0]
+            if len(bad):
+                raise np.linalg.LinAlgError("covariance of object %d is not positive definite" % int(bad[0]))
+            self._results.append({"batch": None, "off": off, "pull": pull, "residual": resid, "prediction": pred,
+                                  "prediction_variance": pvar, "sums": mom, "n": len(pull)})
+        else:
+            batch = DeviceBatch(x_flat, y_flat, off, y0=template, y_err=ye_flat, dim=dim)
+            pred, pvar, pull, resid, info = batch.loo_dev(self.hyperparameters, self.nugget, mode=mode, flags=self.flags)
+            bad = np.nonzero(batch._down(info))[0]
+            if len(bad):
+                raise np.linalg.LinAlgError("covariance of object %d is not positive definite" % int(bad[0]))
+            self._results.append({"batch": batch, "off": off, "pull": pull, "residual": resid, "prediction": pred,
+                                  "prediction_variance": pvar, "n": int(pull.numel())})
         self._host = {}
 
         # scipy.stats.norm.fit (pull.py:102) = sample mean and population standard deviation, over every pull
         # computed so far; reduced on the device (two passes: the mean, then the spread about it)
-        n_tot = sum(int(r["pull"].numel()) for r in self._results)
+        def moments(r, center):
+            """(sum (v - c), sum (v - c)^2) of one call's pulls: reduced on the device, or from the sums the GPUs
+            of a sharded call already reduced"""
+            if r["batch"] is not None:
+                return r["batch"].moments(r["pull"], center)
+            s1, s2 = r["sums"]
+            return s1 - r["n"] * center, s2 - 2.0 * center * s1 + r["n"] * center * center
+
+        n_tot = sum(r["n"] for r in self._results)
         if n_tot:
-            total = sum(r["batch"].moments(r["pull"], 0.0)[0] for r in self._results)
+            total = sum(moments(r, 0.0)[0] for r in self._results)
             self.pull_average = total / n_tot
-            parts = [r["batch"].moments(r["pull"], self.pull_average) for r in self._results]
+            parts = [moments(r, self.pull_average) for r in self._results]
             self.pull_average += sum(p[0] for p in parts) / n_tot          # second-pass correction of the mean
             self.pull_std = float(np.sqrt(sum(p[1] for p in parts) / n_tot
                                           - (sum(p[0] for p in parts) / n_tot) ** 2))
@@ -94,7 +120,7 @@ class build_pull:
     # ---- results, brought to the host when read (10^6 x 40 pulls are 320 MB per array)
     def _flat(self, name):
         if name not in self._host:
-            parts = [r["batch"]._down(r[name]) for r in self._results]
+            parts = [r[name] if r["batch"] is None else r["batch"]._down(r[name]) for r in self._results]
             self._host[name] = parts[0] if len(parts) == 1 else (np.concatenate(parts) if parts else np.zeros(0))
         return self._host[name]
 
@@ -127,4 +153,5 @@ class build_pull:
         """|cov_tt| of the most recent compute_pull call"""
         if not self._results:
             return None
-        return self._results[-1]["batch"]._down(self._results[-1]["prediction_variance"])
+        r = self._results[-1]
+        return r["prediction_variance"] if r["batch"] is None else r["batch"]._down(r["prediction_variance"])

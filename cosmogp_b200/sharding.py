@@ -52,6 +52,45 @@ def allreduce_sum(value, device=None):
     return total
 
 
+def allreduce_sums(values, device=None):
+    """allreduce_sum for a few doubles at once (one exchange): -> list of sums, identical on every rank."""
+    vals = [float(v) for v in values]
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return vals
+    t = torch.tensor(vals, dtype=torch.float64, device=device or "cpu")
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t)
+    rows = torch.stack(parts).cpu().numpy()
+    out = [0.0] * len(vals)
+    for r in rows:                                          # rank order
+        for k in range(len(vals)):
+            out[k] += float(r[k])
+    return out
+
+
+def gather_to_root(local, counts, root=0, device=None):
+    """Final gather of per-rank 1-D float64 arrays (lengths `counts`, known everywhere) on `root` only: every other
+    rank sends its own slice once (point-to-point over NVLink with NCCL), nothing is padded or replicated.
+    -> the concatenation on root, None elsewhere."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return np.asarray(local)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = device or "cpu"
+    mine = torch.as_tensor(np.ascontiguousarray(local, dtype=np.float64)).to(dev)
+    assert mine.numel() == int(counts[rank]), "rank %d: %d values, expected %d" % (rank, mine.numel(), counts[rank])
+    if rank != root:
+        if mine.numel():
+            dist.send(mine, dst=root)
+        return None
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    out = torch.empty(int(starts[-1]), dtype=torch.float64, device=dev)
+    out[starts[root]:starts[root + 1]] = mine
+    for r in range(world):
+        if r != root and counts[r]:
+            dist.recv(out[starts[r]:starts[r + 1]], src=r)
+    return out.cpu().numpy()
+
+
 def gather_ragged(local, counts, device=None):
     """Concatenate per-rank 1-D float64 arrays (lengths `counts`, known everywhere) on every rank."""
     if not (dist.is_initialized() and dist.get_world_size() > 1):

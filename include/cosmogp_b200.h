@@ -82,6 +82,15 @@ int cgp_ll_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
                        const double* hyp, double nugget, double floor, unsigned flags,
                        double* ll_obj, int* info, void* stream);
 /* host buffers; *ll_sum = sum over objects in index order (Gaussian_process.py:205-213). */
+/* The likelihood evaluation as the optimiser sees it (cosmogp/Gaussian_process.py:205-213: the sum over objects):
+ * cgp_ll_batched_dev followed by a reduction on the device.  total_dev[2] (device) receives
+ * { sum of ll_obj in a fixed order, number of objects with info != 0 }; when total_host (pinned host memory, 2 doubles)
+ * is given the 16 bytes are copied there, the stream is synchronised and the return value is the number of
+ * non-positive-definite objects -- one call, 16 bytes over PCIe per simplex point.  ll_obj / info stay on the device. */
+int cgp_ll_total_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                     const double* x, const double* y, const double* y0, const double* y_err,
+                     const double* hyp, double nugget, double floor, unsigned flags,
+                     double* ll_obj, int* info, double* total_dev, double* total_host, void* stream);
 int cgp_ll_batched_host(int64_t n_obj, const int64_t* off, int dim,
                         const double* x, const double* y, const double* y0, const double* y_err,
                         const double* hyp, double nugget, double floor, unsigned flags,
@@ -287,6 +296,43 @@ int cgp_moments_dev(const double* v, int64_t n, double center, double* out2, voi
  * lower_only != 0 computes only the tiles on or below the block diagonal. */
 int cgp_gemm_nt_dev(const double* a, int64_t lda, const double* b, int64_t ldb, double* c, int64_t ldc,
                     int64_t m, int64_t n, int64_t k, double alpha, double beta, int lower_only, void* stream);
+
+/* ---- single-process multi-GPU context: the objects of a batch are sharded over the GPUs of
+ *      one box in contiguous ranges balanced by sum N^3; every GPU keeps its shard resident and runs the kernels of
+ *      the one-GPU entry points; nothing is exchanged on the data path.  What the reference does in ONE Python loop
+ *      over objects (cosmogp/Gaussian_process.py:205-213, :304-335; cosmogp/pull.py:66-94) stays one call with one
+ *      set of host arrays in and out.  NCCL (ncclCommInitAll over the context's devices) is loaded at run time from
+ *      the libnccl.so.2 of the process (PyTorch ships one) or from cgp_set_nccl_library(path); it carries the final
+ *      gather of per-object outputs on device 0 over NVLink (gather = 1) and the scalar all-reduce.
+ *      gather = 0: every device writes its slice of the host outputs over its own PCIe link (no exchange at all).
+ *      Calls on one context are serialised by the caller; each call returns with the host outputs valid. */
+int cgp_set_nccl_library(const char* path);
+int cgp_shard_ranges(int64_t n_obj, const int64_t* off, int n_parts, int64_t* starts /* n_parts + 1 */);   /* host only */
+int cgp_ctx_create(int n_dev /* <= 0: all */, const int* dev_ids /* NULL: 0..n_dev-1 */, void** ctx);
+void cgp_ctx_destroy(void* ctx);
+int cgp_ctx_info(void* ctx, int* n_dev, int* have_nccl);
+/* thin NCCL wrappers on per-device buffers: send_dev[d] (counts[d] doubles on device d) -> recv_root_dev (on device
+ * `root`, sum of counts) by ncclSend / ncclRecv in one group; buf_dev[d] (count doubles each) summed in place. */
+int cgp_ctx_gather_f64(void* ctx, double* const* send_dev, const int64_t* counts, double* recv_root_dev, int root);
+int cgp_ctx_allreduce_sum_f64(void* ctx, double* const* buf_dev, int64_t count);
+/* a batch (HOST arrays, CSR like the *_host entry points) uploaded once and kept resident, shard by shard */
+int cgp_ctx_batch_create(void* ctx, int64_t n_obj, const int64_t* off, int dim,
+                         const double* x, const double* y, const double* y0, const double* y_err, void** batch);
+void cgp_ctx_batch_destroy(void* batch);
+int cgp_ctx_batch_ranges(void* batch, int64_t* starts /* n_dev + 1 */);
+/* compute_log_likelihood (Gaussian_process.py:191-213): one launch + one reduction per device, 16 bytes back from
+ * each, added in device order; ll_obj / info (host, n_obj) may be NULL.  Returns the number of non-PD objects. */
+int cgp_ctx_batch_ll(void* batch, const double* hyp, double nugget, double floor, unsigned flags,
+                     double* ll_sum, double* ll_obj, int* info);
+/* get_prediction on a shared grid (:270-361); with ll_obj != NULL also the likelihood from the same factorisation
+ * (cgp_step_batched_dev).  new_y0: NULL, (n_obj, m), or with CGP_MEAN_TEMPLATE the packed [template (m) | offsets (n_obj)]. */
+int cgp_ctx_batch_predict(void* batch, const double* hyp, double nugget, double floor, unsigned flags,
+                          const double* xnew, int64_t m, const double* new_y0,
+                          double* ll_obj, double* mean, double* var, int* info, int gather);
+/* build_pull.compute_pull (pull.py:43-102) in closed form; the batch's y0 is the template mean.  moments (2 doubles,
+ * may be NULL): sum of the pulls and of their squares (norm.fit, pull.py:102), all-reduced over NVLink when gather = 1. */
+int cgp_ctx_batch_loo(void* batch, const double* hyp, double nugget, double floor, unsigned flags, int mode,
+                      double* pred, double* pred_var, double* pull, double* resid, int* info, double* moments, int gather);
 
 #ifdef __cplusplus
 }

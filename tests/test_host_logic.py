@@ -51,3 +51,18 @@ def test_streamer_chunk_schedule():
     assert len(set(sched(100000, 16667, n_pts=100))) <= 2           # objects beyond the one-warp kernels: equal chunks
     assert L.lib().cgp_streamer_schedule(10, 0, 60, None, 0) == -1
     assert L.lib().cgp_streamer_schedule(100000, 16667, 60, None, 0) == len(s)
+
+
+def test_shard_ranges_cover_and_balance():
+    """cgp_shard_ranges (host only): contiguous ranges, every object exactly once, sum N^3 balanced."""
+    from cosmogp_b200 import multi
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(1, 200, 5000)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    for parts in (1, 2, 3, 8):
+        r = multi.shard_ranges(off, parts)
+        assert r[0][0] == 0 and r[-1][1] == len(sizes) and all(r[i][1] == r[i + 1][0] for i in range(parts - 1))
+        cost = [float((sizes[a:b].astype(float) ** 3).sum()) for a, b in r]
+        assert max(cost) < 1.1 * sum(cost) / parts + 200.0 ** 3
+    assert multi.shard_ranges(np.array([0]), 3) == [(0, 0)] * 3
+    assert multi.shard_ranges(np.array([0, 5]), 4)[0] == (0, 1)
