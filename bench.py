@@ -186,12 +186,131 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}))
 
 
-def workload_config(n_obj, world):
-    return {"workload": "C2: batched 1D light curves, shared mean; step = 1 LL evaluation + predict(mean,var) on shared grid",
-            "objects_per_gpu": n_obj, "epochs": N_EPOCH, "grid_points": M_GRID, "kernel": "RBF1D",
-            "hyp": list(HYP), "nugget": NUGGET, "y_err": YERR, "sharding": "objects x%d, no data-path collective "
-            "(LL sum all-reduced)" % world, "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2"
-            % (n_obj * (4 * N_EPOCH + 3 * M_GRID) * 8 / 1e6)}
+def workload_config(n_obj, world, scaling="weak"):
+    return {"workload": "C2: batched 1D light curves, shared mean; step = one pass of the hot path = log-likelihood of every "
+                        "object + predict(mean, var) on a shared grid at the same hyperparameters (one factorisation per "
+                        "object serves both); NOT a full fit: a fit repeats the likelihood evaluation ~60-80 times "
+                        "(reported as ll_evaluation / facade_e2e)",
+            "objects_per_gpu": n_obj, "objects_total": n_obj * world, "epochs": N_EPOCH, "grid_points": M_GRID, "kernel": "RBF1D",
+            "hyp": list(HYP), "nugget": NUGGET, "y_err": YERR, "scaling_mode": scaling,
+            "sharding": "objects x%d, no data-path collective (LL sum all-reduced)" % world,
+            "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (n_obj * (4 * N_EPOCH + 3 * M_GRID) * 8 / 1e6)
+            if n_obj * (4 * N_EPOCH + 3 * M_GRID) * 8 > 126e6 else
+            "L2 flushed between steps is not needed for the timed kernels' inputs: they are regenerated per object on chip; "
+            "inputs+outputs per step are %.0f MB" % (n_obj * (4 * N_EPOCH + 3 * M_GRID) * 8 / 1e6)}
+
+
+def _facade_worker(args):
+    """The reference doing what facade_e2e does: construct, find_hyperparameters, get_prediction (one core)."""
+    x, y, ye, tmean, ymean, grid = args
+    from threadpoolctl import threadpool_limits
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    with threadpool_limits(limits=1), ref_loader.quiet():
+        t0 = time.perf_counter()
+        gp = ref.gaussian_process_nobject(list(y), list(x), kernel="RBF1D", y_err=list(ye), Mean_Y=ymean, Time_mean=tmean)
+        gp.find_hyperparameters(hyperparameter_guess=[0.4, 3.0], svd_method=False)
+        gp.get_prediction(new_binning=grid, COV=True, svd_method=False)
+        return time.perf_counter() - t0, [float(v) for v in gp.hyperparameters]
+
+
+# ----------------------------------------------------------------------------- C5: leave-one-out pulls, sharded
+def run_c5(args, rank, world, local):
+    """BASELINE config 5: leave-one-out pulls of 10^6 light curves x 40 epochs sharded over the ranks (one per GPU),
+    every rank on its own contiguous range, the per-object outputs gathered on rank 0 by NCCL send/recv over NVLink
+    (cosmogp_b200.sharding.gather_to_root).  value = objects/s with the shards resident (kernel only, max over ranks);
+    e2e = upload of the rank's inputs + kernel + gather of the four output arrays on rank 0 + download there."""
+    import torch
+    import torch.distributed as dist
+    from cosmogp_b200 import _lib, sharding
+    from cosmogp_b200.batch import DeviceBatch
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, total = 40, args.objects if args.objects != 100000 else 1000000
+    ranges = sharding.balanced_ranges(np.full(total, n), world)
+    a, b = ranges[rank]
+    B = b - a
+    rng = np.random.default_rng(5 + rank)                              # SURVEY 8(d) C5 recipe
+    x = np.sort(rng.uniform(-10, 10, (B, n)), axis=1)
+    y = 0.5 * np.sin(x / 2.0 + rng.uniform(0, 2 * np.pi, (B, 1))) + 0.1 * rng.standard_normal((B, n))
+    ye = np.full((B, n), 0.1)
+    hyp, nug = (0.5, 2.0), 0.0
+    off = np.arange(B + 1, dtype=np.int64) * n
+    pin = lambda v: torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+    xp, yp, yep = pin(x.ravel()), pin(y.ravel()), pin(ye.ravel())
+    batch = DeviceBatch(xp.numpy(), yp.numpy(), off, y_err=yep.numpy(), dim=1)
+    for _ in range(max(args.warmup, 3)):
+        outs = batch.loo_dev(hyp, nug)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.lib().cgp_launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        outs = batch.loo_dev(hyp, nug)
+    e1.record(); torch.cuda.synchronize()
+    launches = _lib.lib().cgp_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    # parity of the timed step on every rank: pulls of the first objects against the oracle
+    from oracle import gp_oracle as O
+    po = O.loo_batched_1d(x[:N_CHECK], y[:N_CHECK], ye[:N_CHECK], hyp, nug)
+    got = outs[2][:N_CHECK * n].cpu().numpy()
+    parity = float(np.max(np.abs(got - po[2].ravel()) / np.maximum(np.abs(po[2].ravel()), 1e-3)))
+
+    def e2e_step():
+        bt = DeviceBatch(xp.numpy(), yp.numpy(), off, y_err=yep.numpy(), dim=1)
+        pred, pvar, pull, resid, info = bt.loo_dev(hyp, nug)
+        counts = [(r[1] - r[0]) * n for r in ranges]
+        res = []
+        for t in (pred, pvar, pull, resid):
+            if world > 1:
+                flat = sharding.gather_to_root_dev(t, counts, root=0)
+            else:
+                flat = t
+            if rank == 0:
+                res.append(bt._down(flat, sync=False))
+        torch.cuda.synchronize()
+        return res
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s, parity], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s, parity = (float(v) for v in t.tolist())
+    assert parity < 1e-8, "C5 parity %g" % parity
+    if rank == 0:
+        assert all(len(r) == total * n for r in res)
+        peak = _lib.fp64_peak(1)
+        fl = 2.0 * n ** 3 / 3.0 + 6.0 * n ** 2
+        ach = fl * total * args.steps / (ms * 1e-3) * 1e-12 / world
+        print(json.dumps({
+            "metric": "loo_pull_objects_per_sec", "value": total * args.steps / (ms * 1e-3), "unit": "objects/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C5: leave-one-out pulls, closed form on K^-1; %d objects x %d epochs in total, sharded x%d by "
+                                   "sum N^3, final gather of pred / var / pull / resid on rank 0 by NCCL send/recv" % (total, n, world),
+                       "objects_total": total, "epochs": n, "hyp": list(hyp), "y_err": 0.1},
+            "e2e": {"value": total * e2e_steps / e2e_s, "unit": "objects/s", "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "h2d_bytes_per_step": int(3 * B * n * 8 + (B + 1) * 8), "d2h_bytes_per_step": int(4 * total * n * 8),
+                    "path": "per rank: DeviceBatch upload (pinned) -> cgp_loo_batched_dev -> NCCL gather of 4 arrays on rank 0 -> "
+                            "download on rank 0 (h2d bytes are per rank, d2h bytes leave through rank 0's link)"},
+            "gpu_launches": int(launches), "parity_max_rel_err": parity,
+            "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,LOO,5>", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": ach / peak, "traffic": None, "flop_per_object": fl}}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -201,7 +320,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--objects", type=int, default=100000, help="objects per GPU")
+    ap.add_argument("--objects", type=int, default=100000, help="objects per GPU (weak scaling) or in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --objects per GPU (the contract's default); strong: --objects in total, split over the GPUs")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
     ap.add_argument("--cpu-objects", type=int, default=0, help="objects per CPU baseline pass")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -211,6 +333,8 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.workload == "c5":
+        return run_c5(args, rank, world, local)
 
     import torch
     import torch.distributed as dist
@@ -223,7 +347,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
 
-    B = args.objects
+    B = args.objects if args.scaling == "weak" else args.objects // world
     x, y, ye, tmean, ymean = make_c2(B, 2 + rank)
     off = np.arange(B + 1, dtype=np.int64) * N_EPOCH
     y0, d = M.batched_mean(x.ravel(), y.ravel(), off, 1, ymean, tmean, None)      # host prep, outside the path
@@ -231,9 +355,8 @@ def main():
     # shared mean: template on the grid + one offset per object (the reference's Mean_Y / diff, mean.py:92-101);
     # the device adds them, so M + B doubles travel instead of B x M
     tmpl = M.template_on_grid(grid, 1, ymean, tmean)
-    ny0 = tmpl[None, :] + d[:, None]                                    # the same thing materialised, for the CPU leg
+    ny0 = tmpl[None, :] + d[:, None]                                    # the same thing materialised, for the checker
     packed_mean = np.concatenate([tmpl, d])
-    # pinned host staging (what a caller that cares about PCIe hands us)
     (xp, _k1), (yp, _k2), (y0p, _k3), (yep, _k4), (ny0p, _k5) = (pinned_like(a) for a in (x.ravel(), y.ravel(), y0, ye.ravel(), packed_mean))
 
     batch = DeviceBatch(xp, yp, off, y0=y0p, y_err=yep, dim=1)
@@ -243,20 +366,17 @@ def main():
     peak_dfma = _lib.fp64_peak(0)
 
     def step():
-        ll, info = batch.ll_dev(HYP, NUGGET)
+        # one factorisation per object: the factor kernel also emits the log-likelihood, the grid kernel predicts from the
+        # factor (what cgp_step_batched_dev runs; called as its two halves so that each kernel is timed on its own)
+        fac = batch.factor_dev(HYP, NUGGET, want_ll=True)
         if world > 1:
-            tot = ll.sum()
+            tot = fac["ll"].sum()
             dist.all_reduce(tot)          # the one exchange a likelihood evaluation needs
         e_mid.record()
-        # prediction = factorisation kernel + grid kernel (what cgp_predict_batched_dev runs internally
-        # for large batches; called as two entry points here so that each kernel is timed on its own)
-        fac = batch.factor_dev(HYP, NUGGET)
-        e_mid2.record()
         mean, var, _ = batch.predict_factored_dev(fac, g_dev, None, ny0_dev, True, template_mean=True, uniform_grid=True)
-        return ll, mean, var
+        return fac["ll"], mean, var
 
     e_mid = torch.cuda.Event(enable_timing=True)
-    e_mid2 = torch.cuda.Event(enable_timing=True)
     for _ in range(args.warmup):
         out = step()
     torch.cuda.synchronize()
@@ -266,14 +386,21 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = _lib.lib().cgp_launch_count()
     for k in range(args.steps):
         ev[k][0].record()
-        e_mid, e_mid2 = ev[k][1], ev[k][2]
+        e_mid = ev[k][1]
         out = step()
-        ev[k][3].record()
+        ev[k][2].record()
     torch.cuda.synchronize()
+    launches = _lib.lib().cgp_launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    fa_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    pr_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    clocks = sampler.stop()
     # parity of the TIMED step, on every rank: LL, mean and variance of the first N_CHECK objects against the oracle
     from oracle import gp_oracle as O              # the checker, never the thing measured
     y0m = y0.reshape(B, N_EPOCH)
@@ -284,28 +411,22 @@ def main():
            "var": out[2][:N_CHECK * M_GRID].cpu().numpy().reshape(N_CHECK, M_GRID)}
     rel = lambda a, b: float(np.max(np.abs(a - b) / np.abs(b)))
     parity = max(rel(chk["ll"], ll_o), rel(chk["mean"], mean_o), rel(chk["var"], var_o))
-    launches = _lib.lib().cgp_launch_count() - launches0
-    if world > 1:
-        dist.barrier()
-    total_ms = ev[0][0].elapsed_time(ev[-1][3])
-    ll_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    fa_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    pr_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
-    clocks = sampler.stop()
-    # the same outputs from ONE factorisation per object (the factor kernel also emits the likelihood): what the
-    # end-to-end path runs; reported beside the step, whose separate LL launch is what a fit repeats ~60 times
-    def fused_step():
-        fac = batch.factor_dev(HYP, NUGGET, want_ll=True)
-        return batch.predict_factored_dev(fac, g_dev, None, ny0_dev, True, template_mean=True, uniform_grid=True)
-    fused_step(); fused_step()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    f0.record()
-    for _ in range(max(3, min(args.steps, 10))):
-        fused_step()
-    f1.record()
-    torch.cuda.synchronize()
-    fused_ms = f0.elapsed_time(f1) / max(3, min(args.steps, 10))
+
+    # the likelihood evaluation alone, as the optimiser drives it: the compact LL kernel (its own factorisation, rows retired)
+    # + the device reduction + 16 bytes back; kernel time by CUDA events, wall time of the whole call
+    batch.log_likelihood_total(HYP, NUGGET)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_ll = max(5, args.steps)
+    k0.record()
+    for _ in range(n_ll):
+        batch.ll_dev(HYP, NUGGET)
+    k1.record(); torch.cuda.synchronize()
+    ll_ms = k0.elapsed_time(k1) / n_ll
+    t0 = time.perf_counter()
+    for _ in range(n_ll):
+        ll_tot, _bad = batch.log_likelihood_total(HYP, NUGGET)
+    ll_wall_ms = (time.perf_counter() - t0) / n_ll * 1e3
+    parity = max(parity, abs(ll_tot - float(out[0].sum().item())) / abs(ll_tot))
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -338,57 +459,57 @@ def main():
     e2e_s = time.perf_counter() - t0
     parity = max(parity, rel(ev_e2e.host("ll")[sel], ll_o), rel(ev_e2e.host("mean")[sel], mean_o), rel(ev_e2e.host("var")[sel], var_o))
     if world > 1:
-        t = torch.tensor([parity], device=dev, dtype=torch.float64)
+        t = torch.tensor([parity, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        parity = float(t.item())
+        parity, e2e_s = (float(v) for v in t.tolist())
     assert parity < 1e-9, "rank %d: parity check of the timed step failed: %g" % (rank, parity)
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    traffic = None                      # dram bytes per launch of the predict kernel, from the committed ncu capture
+    traffic, traffic_src = None, None   # DRAM bytes per launch of the dominant kernel: the committed ncu --set full capture
     try:
         if B == 100000:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["predict_f"]["traffic"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic, traffic_src = tj["predict_f"]["traffic"], tj.get("source", "profiles/ncu_traffic.json")
     except Exception:
         pass
     value = B * world * args.steps / (total_ms * 1e-3)
     # dominant kernel = the grid kernel: per grid point h build + mean dot + v = L^-1 h + |v|^2
     fl_grid = M_GRID * (N_EPOCH ** 2 + 8.0 * N_EPOCH)
-    fl_factor = flops_predict(N_EPOCH, M_GRID) - fl_grid
+    fl_factor = flops_predict(N_EPOCH, M_GRID) - fl_grid + 2.0 * N_EPOCH       # + |z|^2 for the likelihood
+    fl_step = fl_grid + fl_factor
     achieved = fl_grid * B / (pr_ms * 1e-3) * 1e-12
     line = {
         "metric": "gp_fits_per_sec", "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B, world),
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B, world, args.scaling),
         "clocks": clocks,
         "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "objects/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
-                "path": "StreamedEvaluator.run -> cgp_streamer_run: pinned host in, pinned host out; per chunk one "
-                        "factorisation serves the likelihood and the prediction (the timed resident step above "
-                        "keeps the separate LL kernel)"},
+                "path": "StreamedEvaluator.run -> cgp_streamer_run: pinned host in, pinned host out; chunks of objects "
+                        "pipelined over upload / compute / download streams; the same two kernels per chunk as the resident step"},
         "gpu_launches": int(launches),
-        "fused_step": {"ms_per_step": fused_ms, "objects_per_s_per_gpu": B / (fused_ms * 1e-3),
-                       "what": "LL + predict from one factorisation per object (factor kernel emits LL), resident"},
         "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,PREDICT_FU,8>: predictive mean+variance on the (uniform) grid "
                      "from the TMA-staged factor (FP64 tensor pipe, DMMA.8x8x4)", "achieved": achieved,
                      "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "peak_source": "FP64 DMMA m8n8k4 ceiling measured in this run (cgp_fp64_peak); MEASURED_PEAKS.json "
                                     "has no FP64 entry; DFMA ceiling %.2f" % peak_dfma,
                      "flop_per_object": fl_grid, "ms_per_launch": pr_ms,
                      "factor_kernel": {"ms_per_launch": fa_ms, "flop_per_object": fl_factor,
-                                       "achieved": fl_factor * B / (fa_ms * 1e-3) * 1e-12},
-                     "ll_kernel": {"ms_per_launch": ll_ms, "flop_per_object": flops_ll(N_EPOCH),
-                                   "achieved": flops_ll(N_EPOCH) * B / (ll_ms * 1e-3) * 1e-12},
-                     "whole_step": {"flop_per_object": flops_ll(N_EPOCH) + flops_predict(N_EPOCH, M_GRID),
-                                    "achieved": (flops_ll(N_EPOCH) + flops_predict(N_EPOCH, M_GRID)) * B * args.steps
-                                    / (total_ms * 1e-3) * 1e-12}},
+                                       "achieved": fl_factor * B / (fa_ms * 1e-3) * 1e-12,
+                                       "frac": fl_factor * B / (fa_ms * 1e-3) * 1e-12 / peak_dmma,
+                                       "what": "covariance + Cholesky + L^-1 + alpha + log-likelihood, spilled for the grid kernel"},
+                     "whole_step": {"flop_per_object": fl_step, "achieved": fl_step * B * args.steps / (total_ms * 1e-3) * 1e-12,
+                                    "frac": fl_step * B * args.steps / (total_ms * 1e-3) * 1e-12 / peak_dmma}},
+        "ll_evaluation": {"kernel_ms": ll_ms, "wall_ms": ll_wall_ms, "flop_per_object": flops_ll(N_EPOCH),
+                          "achieved": flops_ll(N_EPOCH) * B / (ll_ms * 1e-3) * 1e-12,
+                          "frac": flops_ll(N_EPOCH) * B / (ll_ms * 1e-3) * 1e-12 / peak_dmma,
+                          "what": "one simplex point of find_hyperparameters: compact LL kernel; wall = kernel + reduction on the "
+                                  "device + 16 bytes back (DeviceBatch.log_likelihood_total)"},
     }
     line["parity_max_rel_err"] = parity
     line["parity"] = ("every rank: LL, mean and variance of %d objects of its timed resident step and of its end-to-end "
@@ -401,10 +522,16 @@ def main():
         if kind == "reference":
             from oracle import ref_loader
             ref_loader.load()
+        n_fac = 16 * cores
         with mp.get_context("fork").Pool(cores) as pool:
             cpu_pass(kind, False, x[:4 * cores], y[:4 * cores], ye[:4 * cores], tmean, ymean, grid, pool, cores)
             v, res = cpu_pass(kind, False, x[:n_cpu], y[:n_cpu], ye[:n_cpu], tmean, ymean, grid, pool, cores)
             v_svd, _r = cpu_pass(kind, True, x[:n_cpu // 2], y[:n_cpu // 2], ye[:n_cpu // 2], tmean, ymean, grid, pool, cores)
+            fac_ref = None
+            if kind == "reference":
+                parts = np.array_split(np.arange(n_fac), cores)
+                fr = pool.map(_facade_worker, [(x[q], y[q], ye[q], tmean, ymean, grid) for q in parts])
+                fac_ref = n_fac / max(r[0] for r in fr)
         # the CPU leg doubles as a second checker: object 0's prediction by the reference itself against the timed step
         m_ref, v_ref = res[0][2], res[0][3]
         line["parity_vs_cpu_arm"] = float(max(np.max(np.abs(chk["mean"][0] - m_ref) / np.abs(m_ref)),
@@ -418,6 +545,25 @@ def main():
                                               else "oracle port (baseline/_ref absent)", cores),
                                 "svd_method_true": {"value": v_svd, "unit": "objects/s",
                                                     "what": "the reference's default argument, %d objects" % (n_cpu // 2)}}
+        # the public facade used the way a cosmogp user would: construct -> find_hyperparameters -> get_prediction -> numpy (wall)
+        import cosmogp_b200 as cg
+        def facade():
+            gp = cg.gaussian_process_nobject(y, x, y_err=ye, Mean_Y=ymean, Time_mean=tmean)
+            gp.find_hyperparameters(hyperparameter_guess=[0.4, 3.0], svd_method=False)
+            gp.get_prediction(new_binning=grid, COV='diag', svd_method=False)
+            return gp
+        facade()
+        t0 = time.perf_counter()
+        gp = facade()
+        np.asarray(gp.Prediction); np.asarray(gp.prediction_variance)
+        fs = time.perf_counter() - t0
+        line["facade_e2e"] = {"value": B / fs, "unit": "objects/s", "seconds": fs, "fit_hyperparameters": [float(v) for v in gp.hyperparameters],
+                              "what": "gaussian_process_nobject(numpy lists) -> find_hyperparameters (scipy fmin on the host, one device "
+                                      "launch per simplex point) -> get_prediction -> numpy arrays; wall clock, all %d objects" % B,
+                              "reference": None if fac_ref is None else {
+                                  "value": fac_ref, "unit": "objects/s", "cores": cores,
+                                  "what": "the unmodified reference doing the same calls (svd_method=False, COV=True) on %d objects, "
+                                          "%d processes" % (n_fac, cores)}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

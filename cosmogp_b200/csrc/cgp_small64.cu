@@ -152,12 +152,18 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   double* px = tiles + NT * TILE;          // DIM * LD
   double* noise = px + DIM * LD;
   double* vr = noise + LD;                 // r (LL: becomes z)
-  // predict: z overwrites the (dead) noise vector and alpha overwrites r -> same footprint as LL
   constexpr bool PF = TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU;      // predict from a stored factor
   constexpr bool UNI = TASK == TASK_PREDICT_FU || TASK == TASK_PREDICT_U;      // ... on a uniformly spaced shared grid
   constexpr bool FUSED = TASK == TASK_PREDICT || TASK == TASK_PREDICT_U;       // factorise and predict in one pass (no workspace)
   constexpr bool PRED_LIKE = FUSED || TASK == TASK_FACTOR || PF;
-  double* vz = PRED_LIKE ? noise : vr + LD;
+  // Prediction needs no L^-1 (round 2): with the accumulator == operand layout the grid phase solves L v = h by block
+  // FORWARD SUBSTITUTION on the tensor cores -- V_J = (H_J - sum_{P<J} V_P L[J][P]^T) T_J^T, every V_P fed to the next
+  // DMMA straight from its accumulator registers -- at the same DMMA count as a product with L^-1, and the mean is
+  // v . z with z = L^-1 r from the likelihood's forward solve (alpha is never formed).  The factorisation of these
+  // tasks therefore stops after the Cholesky factor; its off-diagonal tiles are stored NEGATED (the products of the
+  // later columns do not notice: (-a)(-b) = ab) so that the grid phase accumulates h + sum V_P (-L)^T directly.
+  constexpr bool NEGL = PRED_LIKE;
+  double* vz = PRED_LIKE ? vr : vr + LD;                // prediction tasks: z = L^-1 r overwrites r in place (block by block)
   double* va = PRED_LIKE ? vr : vz + LD;
   double* vd = va + LD;
   double* v1 = vd + LD;
@@ -347,7 +353,24 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         dmma(s0[i], s1[i], c0, t0); dmma(u0[i], u1[i], c1, t1);
       }
 #pragma unroll
-      for (int i = 1; i < NB - J; ++i) st_frag(tiles, slot(J + i, J), L, s0[i] + u0[i], s1[i] + u1[i]);
+      for (int i = 1; i < NB - J; ++i) {
+        if (NEGL) st_frag(tiles, slot(J + i, J), L, -s0[i] - u0[i], -s1[i] - u1[i]);
+        else st_frag(tiles, slot(J + i, J), L, s0[i] + u0[i], s1[i] + u1[i]);
+      }
+      if (NEGL) {
+        // z_J = T_J (r_J - sum_{P<J} L[J][P] z_P), in place over r (the tiles hold -L): behind the next column's DMMAs
+        double pz = 0.0, pz2 = 0.0;
+#pragma unroll
+        for (int P = 0; P < J; ++P) {
+          const double2 f = ld_frag(tiles, slot(J, P), L);
+          const double2 rv = ld_vec2(vr, 8 * P + 2 * L.t);
+          pz = fma(f.x, rv.x, pz); pz2 = fma(f.y, rv.y, pz2);
+        }
+        const double wv = vr[8 * J + L.g] + red_t(pz + pz2);
+        double q = t0 * __shfl_sync(FULL, wv, L.t * 8) + t1 * __shfl_sync(FULL, wv, L.t * 8 + 4);
+        q = red_t(q);
+        if (L.t == 0) vr[8 * J + L.g] = q;
+      }
       __syncwarp();
     }
 
@@ -379,6 +402,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       continue;
     }
 
+    if constexpr (TASK == TASK_LOO) {
     // ---------------- L^-1 in place, row by row, held TRANSPOSED while it is built: with Xt[J][I] = (L^-1[I][J])^T
     //   Xt[J][I] = -(sum_{P=J..I-1} Xt[J][P] L[I][P]^T) T_I^T,   Xt[J][J] = T_J^T,
     // every product is of the form X*Y^T on natural fragments and the bracket feeds the second product from its
@@ -462,6 +486,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       }
     }
     __syncwarp();
+    }   // TASK_LOO
     if (lane == 0 && part == 0) a.info[b] = bad;
     }   // !PF
 
@@ -487,7 +512,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           a.ll[b] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
         }
       }
-      // ---------------- spill the factor (L^-1 tiles, alpha) for the prediction kernel: 512-byte rows
+      // ---------------- spill the factor (T_J on the diagonal, -L[I][J] below, then z) for the prediction kernel: 512-byte rows
       double* dst = a.fws + b * a.fws_stride;
 #pragma unroll 4
       for (int q = 0; q < NT; ++q)
@@ -557,9 +582,9 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           gx[u] = pgx[u]; gy[u] = pgy[u]; ny0[u] = pny0[u];
         }
         grid_fetch(rb + (int64_t)split * 2);               // next pair's coordinates, behind this pair's math
-        // cross-covariance fragments (no amplitude): 4 NB independent exps per lane
-        double h0[2][NB], h1[2][NB];
-        double pm[2] = {0.0, 0.0}, pm2[2] = {0.0, 0.0};
+        // cross-covariance fragments (no amplitude), generated straight into the accumulators of the forward
+        // substitution: lane (g,t) holds H[grid row g][columns 8P+2t, 8P+2t+1] = the start value of W_P
+        double acc0[2][NB], acc1[2][NB];
         if constexpr (UNI) {
           double2* anch = reinterpret_cast<double2*>(px);      // {E_a, R} per object point (px + noise: 2 LD doubles)
           __syncwarp();                                        // the previous pass has read its anchors
@@ -581,8 +606,6 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           for (int P = 0; P < NB; ++P) {
             const int c0 = 8 * P + 2 * L.t, c1 = c0 + 1;   // this lane's two k-values of block P (see the layout note)
             const double2 A0 = anch[c0], A1 = anch[c1];
-            const double2 al = ld_vec2(va, c0);
-            const double al0 = al.x, al1 = al.y;
             // R^g by squaring (g is fixed per lane: predicated multiplies), R^(g+8) = R^g R^8
             const double r02 = A0.y * A0.y, r04 = r02 * r02, r08 = r04 * r04;
             const double r12 = A1.y * A1.y, r14 = r12 * r12, r18 = r14 * r14;
@@ -592,47 +615,52 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
             const double t0 = A0.x * p0, t1 = A1.x * p1;
             const double e00 = t0 * uni_c0, e01 = (t0 * r08) * uni_c1;
             const double e10 = t1 * uni_c0, e11 = (t1 * r18) * uni_c1;
-            h0[0][P] = e00; h0[1][P] = e01; h1[0][P] = e10; h1[1][P] = e11;
-            pm[0] = fma(e00, al0, pm[0]); pm[1] = fma(e01, al0, pm[1]);
-            pm2[0] = fma(e10, al1, pm2[0]); pm2[1] = fma(e11, al1, pm2[1]);
+            acc0[0][P] = e00; acc0[1][P] = e01; acc1[0][P] = e10; acc1[1][P] = e11;
           }
         } else {
 #pragma unroll
         for (int P = 0; P < NB; ++P) {
           const int c0 = 8 * P + 2 * L.t, c1 = c0 + 1;
-          const double2 xx = ld_vec2(px, c0), al = ld_vec2(va, c0);
+          const double2 xx = ld_vec2(px, c0);
           const double x0 = xx.x, x1 = xx.y;
           double y0c = 0.0, y1c = 0.0;
           if (DIM == 2) { const double2 yy = ld_vec2(px + LD, c0); y0c = yy.x; y1c = yy.y; }
-          const double al0 = al.x, al1 = al.y;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             double e0 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x0, y0c));
             double e1 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x1, y1c));
             e0 = (live[u] && c0 < n) ? e0 : 0.0;
             e1 = (live[u] && c1 < n) ? e1 : 0.0;
-            h0[u][P] = e0; h1[u][P] = e1;
-            pm[u] = fma(e0, al0, pm[u]); pm2[u] = fma(e1, al1, pm2[u]);
+            acc0[u][P] = e0; acc1[u][P] = e1;
           }
         }
         }
-        double acc0[2][NB], acc1[2][NB];
-#pragma unroll
-        for (int J = 0; J < NB; ++J) { acc0[0][J] = 0.0; acc1[0][J] = 0.0; acc0[1][J] = 0.0; acc1[1][J] = 0.0; }
+        // block forward substitution L v = h on the tensor cores (see the NEGL note): block P is finished by
+        // V_P = W_P T_P^T, then added into every later block through the stored -L[J][P]; mean = v . z, var = amp* - |v|^2
+        double pm[2] = {0.0, 0.0}, pm2[2] = {0.0, 0.0}, vs[2] = {0.0, 0.0}, vs2[2] = {0.0, 0.0};
 #pragma unroll
         for (int P = 0; P < NB; ++P) {
+          const double2 ft = ld_frag(tiles, slot(P, P), L);
+          const double2 zz = ld_vec2(va, 8 * P + 2 * L.t);
 #pragma unroll
-          for (int J = P; J < NB; ++J) {
+          for (int u = 0; u < 2; ++u) {
+            double r0 = 0.0, r1 = 0.0, e0 = 0.0, e1 = 0.0;
+            dmma(r0, r1, acc0[u][P], ft.x); dmma(e0, e1, acc1[u][P], ft.y);
+            const double v0 = r0 + e0, v1 = r1 + e1;
+            acc0[u][P] = v0; acc1[u][P] = v1;
+            pm[u] = fma(v0, zz.x, pm[u]); pm2[u] = fma(v1, zz.y, pm2[u]);
+            vs[u] = fma(v0, v0, vs[u]); vs2[u] = fma(v1, v1, vs2[u]);
+          }
+#pragma unroll
+          for (int J = P + 1; J < NB; ++J) {
             const double2 fb = ld_frag(tiles, slot(J, P), L);
-            dmma(acc0[0][J], acc1[0][J], h0[0][P], fb.x); dmma(acc0[1][J], acc1[1][J], h0[1][P], fb.x);
-            dmma(acc0[0][J], acc1[0][J], h1[0][P], fb.y); dmma(acc0[1][J], acc1[1][J], h1[1][P], fb.y);
+            dmma(acc0[0][J], acc1[0][J], acc0[0][P], fb.x); dmma(acc0[1][J], acc1[1][J], acc0[1][P], fb.x);
+            dmma(acc0[0][J], acc1[0][J], acc1[0][P], fb.y); dmma(acc0[1][J], acc1[1][J], acc1[1][P], fb.y);
           }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          double vv = 0.0, vv2 = 0.0;
-#pragma unroll
-          for (int J = 0; J < NB; ++J) { vv = fma(acc0[u][J], acc0[u][J], vv); vv2 = fma(acc1[u][J], acc1[u][J], vv2); }
+          double vv = vs[u], vv2 = vs2[u];
           const double pmt = red_t(pm[u] + pm2[u]);
           vv = red_t(vv + vv2);
           if (live[u] && L.t == 0) {

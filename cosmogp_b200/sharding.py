@@ -91,6 +91,26 @@ def gather_to_root(local, counts, root=0, device=None):
     return out.cpu().numpy()
 
 
+def gather_to_root_dev(local, counts, root=0):
+    """gather_to_root for a DEVICE tensor, result left on the root's device (None elsewhere): the final gather of
+    per-object outputs over NVLink (NCCL point-to-point; every rank sends its slice exactly once)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    assert local.numel() == int(counts[rank])
+    if rank != root:
+        if local.numel():
+            dist.send(local.contiguous(), dst=root)
+        return None
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    out = torch.empty(int(starts[-1]), dtype=local.dtype, device=local.device)
+    out[starts[root]:starts[root + 1]] = local
+    for r in range(world):
+        if r != root and counts[r]:
+            dist.recv(out[starts[r]:starts[r + 1]], src=r)
+    return out
+
+
 def gather_ragged(local, counts, device=None):
     """Concatenate per-rank 1-D float64 arrays (lengths `counts`, known everywhere) on every rank."""
     if not (dist.is_initialized() and dist.get_world_size() > 1):

@@ -40,6 +40,16 @@ def _worker(rank, world, port, q):
     total = sharding.allreduce_sum(ll.sum())
     counts = [r[1] - r[0] for r in sharding.balanced_ranges(sizes, world)]
     allll = sharding.gather_ragged(ll, counts)
+    # the final gather on one rank only (what build_pull / C5 uses): point-to-point, nothing padded or replicated
+    rooted = sharding.gather_to_root(ll, counts, root=0)
+    assert (rooted is None) == (rank != 0)
+    if rank == 0:
+        assert np.array_equal(rooted, allll)
+    t, nb = sharding.allreduce_sums([ll.sum(), float(rank + 1)])
+    assert nb == 3.0 and abs(t - total) <= 1e-12 * abs(total)
+    import torch
+    dev_g = sharding.gather_to_root_dev(torch.from_numpy(ll), counts, root=0)
+    assert (dev_g is None) == (rank != 0) and (rank != 0 or np.array_equal(dev_g.numpy(), allll))
     if rank == 0:
         ref = np.array([O.log_likelihood(y[off[i]:off[i + 1]], x[off[i]:off[i + 1]], [0.7, 3.0], 0.05,
                                          ye[off[i]:off[i + 1]]) for i in range(len(sizes))])
