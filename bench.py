@@ -260,38 +260,50 @@ def run_c5(args, rank, world, local):
     got = outs[2][:N_CHECK * n].cpu().numpy()
     parity = float(np.max(np.abs(got - po[2].ravel()) / np.maximum(np.abs(po[2].ravel()), 1e-3)))
 
-    def e2e_step():
+    counts = [(r[1] - r[0]) * n for r in ranges]
+    host_all = [torch.empty(total * n, dtype=torch.float64, pin_memory=True) for _ in range(4)] if rank == 0 else None
+    host_mine = [torch.empty(B * n, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+
+    def e2e_step(gather):
+        """upload this rank's inputs (pinned) -> kernel -> outputs to the host: gather=True collects the four arrays on
+        rank 0 with NCCL send/recv over NVLink and downloads them there (north_star's final gather); gather=False lets
+        every rank download its own slice over its own PCIe link"""
         bt = DeviceBatch(xp.numpy(), yp.numpy(), off, y_err=yep.numpy(), dim=1)
         pred, pvar, pull, resid, info = bt.loo_dev(hyp, nug)
-        counts = [(r[1] - r[0]) * n for r in ranges]
-        res = []
-        for t in (pred, pvar, pull, resid):
-            if world > 1:
+        for k, t in enumerate((pred, pvar, pull, resid)):
+            if gather and world > 1:
                 flat = sharding.gather_to_root_dev(t, counts, root=0)
+                if rank == 0:
+                    host_all[k].copy_(flat, non_blocking=True)
+            elif gather:
+                host_all[k].copy_(t, non_blocking=True)
             else:
-                flat = t
-            if rank == 0:
-                res.append(bt._down(flat, sync=False))
+                host_mine[k].copy_(t, non_blocking=True)
         torch.cuda.synchronize()
-        return res
-    e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
+
+    def timed_e2e(gather):
+        e2e_step(gather)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step(gather)
+        if world > 1:
+            dist.barrier()
+        return time.perf_counter() - t0
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        res = e2e_step()
+    e2e_s = timed_e2e(True)
+    direct_s = timed_e2e(False)
+    if rank == 0:                                           # the gathered pulls are the oracle's on rank 0's own range
+        got_g = host_all[2][:N_CHECK * n].numpy()
+        parity = max(parity, float(np.max(np.abs(got_g - po[2].ravel()) / np.maximum(np.abs(po[2].ravel()), 1e-3))))
     if world > 1:
-        dist.barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([ms, e2e_s, parity], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, parity, direct_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, parity = (float(v) for v in t.tolist())
+        ms, e2e_s, parity, direct_s = (float(v) for v in t.tolist())
     assert parity < 1e-8, "C5 parity %g" % parity
     if rank == 0:
-        assert all(len(r) == total * n for r in res)
         peak = _lib.fp64_peak(1)
         fl = 2.0 * n ** 3 / 3.0 + 6.0 * n ** 2
         ach = fl * total * args.steps / (ms * 1e-3) * 1e-12 / world
@@ -305,7 +317,9 @@ def run_c5(args, rank, world, local):
             "e2e": {"value": total * e2e_steps / e2e_s, "unit": "objects/s", "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "h2d_bytes_per_step": int(3 * B * n * 8 + (B + 1) * 8), "d2h_bytes_per_step": int(4 * total * n * 8),
                     "path": "per rank: DeviceBatch upload (pinned) -> cgp_loo_batched_dev -> NCCL gather of 4 arrays on rank 0 -> "
-                            "download on rank 0 (h2d bytes are per rank, d2h bytes leave through rank 0's link)"},
+                            "download on rank 0 (h2d bytes are per rank, d2h bytes leave through rank 0's link)",
+                    "without_gather": {"value": total * e2e_steps / direct_s, "unit": "objects/s", "ms_per_step": direct_s / e2e_steps * 1e3,
+                                       "what": "every rank downloads its own slice over its own PCIe link instead"}},
             "gpu_launches": int(launches), "parity_max_rel_err": parity,
             "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,LOO,5>", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                          "frac": ach / peak, "traffic": None, "flop_per_object": fl}}))
@@ -458,10 +472,29 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     parity = max(parity, rel(ev_e2e.host("ll")[sel], ll_o), rel(ev_e2e.host("mean")[sel], mean_o), rel(ev_e2e.host("var")[sel], var_o))
+    # what the box's host side gives N ranks moving data in both directions at the same time (the bound of the end-to-end
+    # leg beyond one GPU: tools/pcie_probe.py is the long form of this)
+    npb = 8 * 1024 * 1024
+    hb_in = torch.empty(npb, dtype=torch.float64, pin_memory=True).fill_(1.0); hb_out = torch.empty(npb, dtype=torch.float64, pin_memory=True)
+    db_in = torch.empty(npb, dtype=torch.float64, device=dev); db_out = torch.ones(npb, dtype=torch.float64, device=dev)
+    sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    def duplex(reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(sa): db_in.copy_(hb_in, non_blocking=True)
+            with torch.cuda.stream(sb): hb_out.copy_(db_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+    duplex(2)
+    duplex_s = duplex(6)
     if world > 1:
-        t = torch.tensor([parity, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([parity, e2e_s, duplex_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        parity, e2e_s = (float(v) for v in t.tolist())
+        parity, e2e_s, duplex_s = (float(v) for v in t.tolist())
+    duplex_gbs = npb * 8 / duplex_s / 1e9
     assert parity < 1e-9, "rank %d: parity check of the timed step failed: %g" % (rank, parity)
 
     if rank != 0:
@@ -490,7 +523,11 @@ def main():
         "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "objects/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
                 "path": "StreamedEvaluator.run -> cgp_streamer_run: pinned host in, pinned host out; chunks of objects "
-                        "pipelined over upload / compute / download streams; the same two kernels per chunk as the resident step"},
+                        "pipelined over upload / compute / download streams; the same two kernels per chunk as the resident step",
+                "host_link": {"duplex_GBps_per_rank_each_direction": duplex_gbs, "ranks_at_once": world,
+                              "transfer_bound_ms_per_step": max(int(h2d), int(d2h)) / (duplex_gbs * 1e9) * 1e3,
+                              "what": "64 MB pinned copies in both directions on every rank at the same time, measured in this run: "
+                                      "the step cannot be faster than its larger direction at this rate"}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,PREDICT_FU,8>: predictive mean+variance on the (uniform) grid "
                      "from the TMA-staged factor (FP64 tensor pipe, DMMA.8x8x4)", "achieved": achieved,

@@ -91,33 +91,47 @@ __device__ __forceinline__ double rbf_arg(const Cov& c, double ax, double ay, do
   return fma(dy * c.h11, dy, fma(dx, c.h00, dy * c.h01) * dx);
 }
 
-// 8x8 Cholesky of a diagonal tile in accumulator layout + T = L^-1 by the same row operations
-// on an identity (see cgp_small.cu).  Rolled loop: 8 call sites share ~60 instructions each.
+// 8x8 Cholesky of a diagonal tile in accumulator layout + T = L^-1 by the same row operations on an identity
+// (see cgp_small.cu).  ONE out-of-line copy per kernel with the eight pivot steps unrolled (static k: shuffle
+// sources, the a0/a1 choice and the row predicates become immediates -- about half the instructions of the
+// rolled loop), arguments and results in registers.  Inlined at its 8 call sites the unrolled form is 46 KB of
+// code and the kernels stall on instruction fetch (the L1.5 instruction cache holds 32 KB).
+struct DiagOut { double t0, t1, piv; int badk; };
+template <int K>
+__device__ __forceinline__ void diag_step(double& a0, double& a1, double& t0, double& t1, double& pivprod, int& badk,
+                                          const int g, const int t) {
+  constexpr int kc = K >> 1;
+  const double ak = (K & 1) ? a1 : a0;
+  const double d = __shfl_sync(FULL, ak, K * 4 + kc);
+  if (!(d > 0.0) && badk == 0) badk = K + 1;
+  const double rinv = cgp_rsqrt(d);
+  pivprod *= d;
+  const double lg = __shfl_sync(FULL, ak, g * 4 + kc) * rinv;
+  // row K of the (symmetric) tile and of T sit in lane (K, t): both operands of the update come from one source lane
+  const double lc0 = __shfl_sync(FULL, a0, K * 4 + t) * rinv;
+  const double lc1 = __shfl_sync(FULL, a1, K * 4 + t) * rinv;
+  a0 = fma(-lg, lc0, a0); a1 = fma(-lg, lc1, a1);
+  const double tk0 = __shfl_sync(FULL, t0, K * 4 + t) * rinv;
+  const double tk1 = __shfl_sync(FULL, t1, K * 4 + t) * rinv;
+  const double f = (g > K) ? lg : 0.0;
+  const double n0 = fma(-f, tk0, t0), n1 = fma(-f, tk1, t1);
+  t0 = (g == K) ? tk0 : n0; t1 = (g == K) ? tk1 : n1;
+}
+__device__ __noinline__ DiagOut diag_factor_impl(double a0, double a1, int g, int t) {
+  double t0 = (g == 2 * t) ? 1.0 : 0.0;
+  double t1 = (g == 2 * t + 1) ? 1.0 : 0.0;
+  double pivprod = 1.0; int badk = 0;
+  diag_step<0>(a0, a1, t0, t1, pivprod, badk, g, t); diag_step<1>(a0, a1, t0, t1, pivprod, badk, g, t);
+  diag_step<2>(a0, a1, t0, t1, pivprod, badk, g, t); diag_step<3>(a0, a1, t0, t1, pivprod, badk, g, t);
+  diag_step<4>(a0, a1, t0, t1, pivprod, badk, g, t); diag_step<5>(a0, a1, t0, t1, pivprod, badk, g, t);
+  diag_step<6>(a0, a1, t0, t1, pivprod, badk, g, t); diag_step<7>(a0, a1, t0, t1, pivprod, badk, g, t);
+  DiagOut o; o.t0 = t0; o.t1 = t1; o.piv = pivprod; o.badk = badk;
+  return o;
+}
 __device__ __forceinline__ void diag_factor(double a0, double a1, const Lane& L,
                                             double& t0, double& t1, double& pivprod, int& badk) {
-  t0 = (L.g == 2 * L.t) ? 1.0 : 0.0;
-  t1 = (L.g == 2 * L.t + 1) ? 1.0 : 0.0;
-  pivprod = 1.0; badk = 0;
-#pragma unroll 1
-  for (int k = 0; k < 8; ++k) {
-    const int kc = k >> 1;
-    const double ak = (k & 1) ? a1 : a0;
-    const double d = __shfl_sync(FULL, ak, k * 4 + kc);
-    if (!(d > 0.0) && badk == 0) badk = k + 1;
-    const double rinv = cgp_rsqrt(d);
-    pivprod *= d;
-    const double lg = __shfl_sync(FULL, ak, L.g * 4 + kc) * rinv;
-    const double lc0 = __shfl_sync(FULL, ak, (2 * L.t) * 4 + kc) * rinv;
-    const double lc1 = __shfl_sync(FULL, ak, (2 * L.t + 1) * 4 + kc) * rinv;
-    a0 = fma(-lg, lc0, a0); a1 = fma(-lg, lc1, a1);
-    const double tk0 = __shfl_sync(FULL, t0, k * 4 + L.t) * rinv;
-    const double tk1 = __shfl_sync(FULL, t1, k * 4 + L.t) * rinv;
-    // branch-free row operation on T: rows above k keep their value (coefficient 0), row k takes the
-    // scaled pivot row (ncu r01f: the branchy form cost 544 register moves per object)
-    const double f = (L.g > k) ? lg : 0.0;
-    const double n0 = fma(-f, tk0, t0), n1 = fma(-f, tk1, t1);
-    t0 = (L.g == k) ? tk0 : n0; t1 = (L.g == k) ? tk1 : n1;
-  }
+  const DiagOut o = diag_factor_impl(a0, a1, L.g, L.t);
+  t0 = o.t0; t1 = o.t1; pivprod = o.piv; badk = o.badk;
 }
 
 // Ring of work counters (one per launch in flight), zeroed in stream order before each launch.
