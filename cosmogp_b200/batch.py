@@ -387,6 +387,39 @@ class DeviceBatch:
             var_h = var_h.reshape(self.n_obj, m) if want_var else None
         return mean_h, var_h, info_h
 
+    def covariance(self, hyp, nugget, grid=None, objects=None, floor=0.0, flags=0):
+        """covariance_matrix of the objects [i0, i1) (default: all) in ONE call (cgp_covariance_batched_dev):
+        grid given (host array, shared by all objects) -> (k, M, M) host array; grid None -> every object on its own
+        epochs (new_binning=None) -> list of (N_b, N_b) host arrays.  Objects of <= 64 points."""
+        i0, i1 = (0, self.n_obj) if objects is None else (int(objects[0]), int(objects[1]))
+        k = i1 - i0
+        h = self._hyp(hyp)
+        own = grid is None
+        if own:
+            g, goff, m = self.x, self.off, 0
+            sizes = np.diff(self.off_host[i0:i1 + 1])
+            coff_h = np.zeros(self.n_obj + 1, dtype=np.int64)
+            coff_h[i0 + 1:i1 + 1] = np.cumsum(sizes * sizes)
+            coff, tot = self._up(coff_h), int(coff_h[i1])
+            goff_ptr, goff_host_ptr, coff_ptr = goff.data_ptr() + 8 * i0, self.off_host.ctypes.data + 8 * i0, coff.data_ptr() + 8 * i0
+        else:
+            g = self._up(np.asarray(grid, dtype=np.float64))
+            m = int(g.shape[0]); tot = k * m * m
+            goff_ptr = goff_host_ptr = coff_ptr = None
+        out = torch.empty(max(tot, 1), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().cgp_covariance_batched_dev(k, self.off.data_ptr() + 8 * i0, self.max_n, self.dim, self._p(self.x),
+                                                       self._p(self.y_err), _lib.hptr(h), float(nugget), float(floor), int(flags),
+                                                       self._p(g), goff_ptr, goff_host_ptr, m, self._p(out), coff_ptr,
+                                                       self._info.data_ptr() + 4 * i0, self._stream())
+        _lib.check(rc, "cgp_covariance_batched_dev")
+        flat = self._down(out[:tot], sync=False)
+        info = self._down(self._info[i0:i1], sync=False)
+        self._sync()
+        if own:
+            return [flat[coff_h[i] :coff_h[i + 1]].reshape(sizes[i - i0], sizes[i - i0]) for i in range(i0, i1)], info
+        return flat.reshape(k, m, m), info
+
     def loo_dev(self, hyp, nugget, mean=None, mode=_lib.CGP_LOO_PLAIN, floor=0.0, flags=0):
         """Closed-form leave-one-out; `mean` (flat, host) replaces the batch's y0 when given.
         -> pred, pred_var, pull, resid (flat DEVICE tensors), info (device)."""

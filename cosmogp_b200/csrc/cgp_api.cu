@@ -568,6 +568,62 @@ int cgp_loo_batched_host(int64_t n_obj, const int64_t* off, int dim,
   return count_bad(info, n_obj);
 }
 
+// ------------------------------------------------------------------------------------ predictive covariance, in bulk
+int cgp_covariance_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                               const double* x, const double* y_err,
+                               const double* hyp, double nugget, double floor, unsigned flags,
+                               const double* xnew, const int64_t* goff, const int64_t* goff_host, int64_t m_shared,
+                               double* cov, const int64_t* coff, int* info, void* stream) {
+  if (n_obj < 0 || (n_obj && (!off || !x || !xnew || !cov || !info))) return fail(CGP_ERR_ARG, "cgp_covariance_batched_dev: NULL argument");
+  if (goff && (!goff_host || !coff)) return fail(CGP_ERR_ARG, "cgp_covariance_batched_dev: per-object grids need goff_host and coff");
+  if (max_n <= 0 || max_n > 64) return fail(CGP_ERR_SIZE, "cgp_covariance_batched_dev: objects of 1..64 points (max_n = %d); larger ones go "
+                                            "through cgp_cov_matrix_dev / cgp_trsm_rows_dev / cgp_gemm_nt_dev", max_n);
+  if (n_obj == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  SmallArgs a; memset(&a, 0, sizeof a);
+  int rc = make_cov(dim, hyp, nugget, floor, flags, &a.cov);
+  if (rc) return rc;
+  const int nb = (max_n + 7) / 8, ldv = 8 * nb;
+  keep_pool_memory();
+  // chunks of objects bound the workspace of V rows (512 MB) and the z dimension of the gram launch
+  const int64_t max_rows = ((int64_t)512 << 20) / (ldv * 8);
+  int64_t c0 = 0;
+  while (c0 < n_obj && !rc) {
+    int64_t c1 = c0, rows = 0, m_max = 0;
+    while (c1 < n_obj && c1 - c0 < 65535) {
+      const int64_t m = goff ? goff_host[c1 + 1] - goff_host[c1] : m_shared;
+      if (c1 > c0 && rows + m > max_rows) break;
+      rows += m; if (m > m_max) m_max = m; ++c1;
+    }
+    double *vws = nullptr, *dummy = nullptr;
+    cudaError_t ce = cudaMallocAsync((void**)&vws, (size_t)(rows ? rows : 1) * ldv * sizeof(double), st);
+    if (ce == cudaSuccess) ce = cudaMallocAsync((void**)&dummy, (size_t)(rows ? rows : 1) * sizeof(double), st);
+    if (ce != cudaSuccess) { if (vws) cudaFreeAsync(vws, st); return cuda_fail((int)ce, "cgp_covariance_batched_dev (workspace)"); }
+    const int64_t row0 = goff ? goff_host[c0] : 0;          // per-object grids index rows absolutely: shift the bases
+    SmallArgs f = a;
+    f.n_obj = c1 - c0; f.off = off + c0; f.x = x; f.y = x; f.yerr = y_err; f.info = info + c0;
+    f.xnew = xnew; f.goff = goff ? goff + c0 : nullptr; f.m_shared = m_shared;
+    f.mean = dummy - row0; f.vout = vws - row0 * ldv;
+    int split = 1;
+    if (!goff && f.n_obj < 296) {
+      const int64_t rbs = (m_shared + 7) / 8;
+      int64_t want = 592 / f.n_obj, cap = (rbs + 3) / 4;
+      if (want > cap) want = cap;
+      if (want > 1) split = (int)want;
+    }
+    f.split = split;
+    rc = run_small(TASK_PREDICT, dim, max_n, f, st, "cgp_covariance_batched_dev (factor)");
+    if (!rc) {
+      int e = large_cov_gram(dim, a.cov, xnew, goff ? goff + c0 : nullptr, goff ? m_max : m_shared, c1 - c0, vws - row0 * ldv, ldv,
+                             info + c0, goff ? cov : cov + c0 * m_shared * m_shared, goff ? coff + c0 : nullptr, st);
+      if (e) rc = cuda_fail(e, "cgp_covariance_batched_dev (gram)");
+    }
+    cudaFreeAsync(vws, st); cudaFreeAsync(dummy, st);
+    c0 = c1;
+  }
+  return rc;
+}
+
 // ------------------------------------------------------------------------------------ matrices
 int cgp_matrices_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
                              const double* x, const double* y_err,

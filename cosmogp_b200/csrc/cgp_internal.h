@@ -90,6 +90,9 @@ struct SmallArgs {
   // leading dimension lda, lower triangle) instead of being generated from x (blocked large-object path)
   const double* amat; const int64_t* aoff; int64_t lda;
   double* logdet;          // TASK_MATRICES: sum of log pivots per object (may be null)
+  // TASK_PREDICT (N <= 64 kernel): when non-null, row (out0 + m) of vout (8 NB doubles per row) receives
+  // v = L^-1 e(x*_m, .) of grid point m (unit amplitude) -- the factor of the bulk predictive-covariance writer
+  double* vout;
 };
 
 struct GemmArgs {          // C[m x n] = beta*C + alpha * A[m x k] * B[n x k]^T, all row-major
@@ -115,6 +118,9 @@ int large_spline_mean(const double* t, const double* c, int nt, const double* x,
                       int64_t n_obj, const double* diff, double* out, cudaStream_t st);
 int large_moments(const double* v, int64_t n, double center, double* out2, cudaStream_t st);
 int large_ll_total(const double* ll, const int* info, int64_t n, double* out2, cudaStream_t st);
+// cov[b] = amp_auto K(g,g) + nugget^2 I - amp_cross^2 V_b V_b^T for objects b of a chunk (V rows from SmallArgs::vout, ldv doubles)
+int large_cov_gram(int dim, const Cov& cov, const double* grid, const int64_t* goff, int64_t m_shared, int64_t n_obj,
+                   const double* v, int ldv, const int* info, double* out, const int64_t* coff, cudaStream_t st);
 int large_dot_sq(const double* v, int64_t n, double* out, cudaStream_t st);
 int large_residual(const double* y, const double* y0, int64_t n, int64_t n_pad, double* r, cudaStream_t st);
 

@@ -727,6 +727,85 @@ int large_ll_total(const double* ll, const int* info, int64_t n, double* out2, c
   cudaFreeAsync(partial, st);
   return (int)cudaGetLastError();
 }
+// Predictive covariance of one object from V = rows L^-1 e(x*_m, .):  C = amp_auto K(g,g) + nugget^2 I - amp_cross^2 V V^T
+// (cosmogp/Gaussian_process.py:356-361).  One CTA per 64 x 64 block: V_i^T and V_j^T staged in shared memory
+// (k-major, so that a thread's four rows are 32 contiguous bytes), 4 x 4 outputs per thread, K(g_i, g_j) generated
+// on the fly.  8 bytes written per ~64 FMAs + one exp: bound by the HBM write of the M x M matrices.
+template <int DIM>
+__global__ void __launch_bounds__(256) cov_gram_kernel(Cov cov, const double* __restrict__ grid, const int64_t* __restrict__ goff,
+                                                       int64_t m_shared, const double* __restrict__ v, int ldv,
+                                                       const int* __restrict__ info, double* __restrict__ out,
+                                                       const int64_t* __restrict__ coff) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t b = blockIdx.z;
+  const int64_t g0 = goff ? goff[b] : 0;
+  const int64_t m = goff ? goff[b + 1] - g0 : m_shared;
+  const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
+  if (i0 >= m || j0 >= m) return;
+  const int64_t row0 = goff ? g0 : b * m_shared;            // first row of this object's V / grid block
+  constexpr int LDS_ = 66;                                  // k-major rows of 64 + 2: 16-byte aligned, transposing stores spread over banks
+  double* vi = sm; double* vj = sm + (size_t)ldv * LDS_;    // [k][64]
+  for (int e = threadIdx.x; e < 64 * ldv; e += 256) {
+    const int r = e / ldv, k = e - r * ldv;                 // coalesced reads of V rows
+    vi[k * LDS_ + r] = (i0 + r < m) ? v[(row0 + i0 + r) * ldv + k] : 0.0;
+    vj[k * LDS_ + r] = (j0 + r < m) ? v[(row0 + j0 + r) * ldv + k] : 0.0;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+  for (int k = 0; k < ldv; ++k) {
+    const double2 a0 = *reinterpret_cast<const double2*>(vi + k * LDS_ + ty * 4), a1 = *reinterpret_cast<const double2*>(vi + k * LDS_ + ty * 4 + 2);
+    const double2 b0 = *reinterpret_cast<const double2*>(vj + k * LDS_ + tx * 4), b1 = *reinterpret_cast<const double2*>(vj + k * LDS_ + tx * 4 + 2);
+    const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+  }
+  const bool bad = info && info[b] != 0;
+  const double a2 = cov.amp_cross * cov.amp_cross;
+  double* ob = out + (coff ? coff[b] : b * m_shared * m_shared);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t i = i0 + ty * 4 + r;
+    if (i >= m) continue;
+    const double xi = grid[(g0 + i) * DIM], yi = DIM == 2 ? grid[(g0 + i) * DIM + 1] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t j = j0 + tx * 4 + c;
+      if (j >= m) continue;
+      const double dx = xi - grid[(g0 + j) * DIM];
+      double q = dx * dx * cov.h00;
+      if (DIM == 2) { const double dy = yi - grid[(g0 + j) * DIM + 1]; q = fma(dy * cov.h11, dy, fma(dx, cov.h00, dy * cov.h01) * dx); }
+      double kk = (i == j) ? cov.amp_auto + cov.nugget2 : cov.amp_auto * cgp_exp(q);
+      ob[i * m + j] = bad ? nan("") : fma(-a2, acc[r][c], kk);
+    }
+  }
+}
+int large_cov_gram(int dim, const Cov& cov, const double* grid, const int64_t* goff, int64_t m_shared, int64_t n_obj,
+                   const double* v, int ldv, const int* info, double* out, const int64_t* coff, cudaStream_t st) {
+  if (n_obj <= 0 || m_shared <= 0) return 0;               // m_shared: the largest grid of the chunk (the grid's x / y extent)
+  const size_t smem = (size_t)2 * 66 * ldv * sizeof(double);
+  const unsigned nb = (unsigned)((m_shared + 63) / 64);
+  if (n_obj > 65535) return (int)cudaErrorInvalidValue;
+  const dim3 g(nb, nb, (unsigned)n_obj);
+  cudaError_t e;
+  if (dim == 1) {
+    e = cudaFuncSetAttribute(cov_gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cov_gram_kernel<1><<<g, 256, smem, st>>>(cov, grid, goff, goff ? 0 : m_shared, v, ldv, info, out, coff);
+  } else {
+    e = cudaFuncSetAttribute(cov_gram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cov_gram_kernel<2><<<g, 256, smem, st>>>(cov, grid, goff, goff ? 0 : m_shared, v, ldv, info, out, coff);
+  }
+  count_launch();
+  return (int)cudaGetLastError();
+}
 int large_sum(const double* v, int64_t n, double* out, cudaStream_t st) {
   sum_kernel<<<1, 1024, 0, st>>>(v, n, out); count_launch(); return (int)cudaGetLastError();
 }

@@ -107,9 +107,10 @@ __device__ __forceinline__ void diag_step(double& a0, double& a1, double& t0, do
   const double rinv = cgp_rsqrt(d);
   pivprod *= d;
   const double lg = __shfl_sync(FULL, ak, g * 4 + kc) * rinv;
-  // row K of the (symmetric) tile and of T sit in lane (K, t): both operands of the update come from one source lane
-  const double lc0 = __shfl_sync(FULL, a0, K * 4 + t) * rinv;
-  const double lc1 = __shfl_sync(FULL, a1, K * 4 + t) * rinv;
+  // column K again, for the columns this lane owns (only the lower triangle of the tile is meaningful: the
+  // covariance tiles are generated with a zero upper triangle, so row K cannot stand in for column K)
+  const double lc0 = __shfl_sync(FULL, ak, (2 * t) * 4 + kc) * rinv;
+  const double lc1 = __shfl_sync(FULL, ak, (2 * t + 1) * 4 + kc) * rinv;
   a0 = fma(-lg, lc0, a0); a1 = fma(-lg, lc1, a1);
   const double tk0 = __shfl_sync(FULL, t0, K * 4 + t) * rinv;
   const double tk1 = __shfl_sync(FULL, t1, K * 4 + t) * rinv;
@@ -662,6 +663,8 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
             dmma(r0, r1, acc0[u][P], ft.x); dmma(e0, e1, acc1[u][P], ft.y);
             const double v0 = r0 + e0, v1 = r1 + e1;
             acc0[u][P] = v0; acc1[u][P] = v1;
+            if (TASK == TASK_PREDICT && a.vout && live[u])      // bulk covariance writer: keep v (16 bytes per lane, 64-byte rows per quad)
+              *reinterpret_cast<double2*>(a.vout + (out0 + mi[u]) * LD + 8 * P + 2 * L.t) = make_double2(v0, v1);
             pm[u] = fma(v0, zz.x, pm[u]); pm2[u] = fma(v1, zz.y, pm2[u]);
             vs[u] = fma(v0, v0, vs[u]); vs2[u] = fma(v1, v1, vs2[u]);
           }
@@ -755,7 +758,7 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   for (;; w = w_nxt, w_nxt = __shfl_sync(FULL, t_next, 0)) {
     if (w >= n_work) break;
     if (lane == 0) t_next = (int64_t)atomicAdd(ticket, 1ULL) + 2 * (int64_t)gridDim.x;
-    const int64_t io = nx.io;
+    const int64_t io = nx.io, nx_b = nx.b;
     const int n = nx.n;
     if (a.hyp_obj) cov = cov_from_hyp(DIM, a.hyp_obj + io * a.n_hyp, a.nugget_obj ? a.nugget_obj[io] : a.nugget_shared,
                                       a.floor_shared, a.flags);
@@ -774,6 +777,8 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     __syncwarp();
 
     double lp_m = 1.0, quad = 0.0; int lp_e = 0; int bad = 0;
+    constexpr int NTF = NB * (NB + 1) / 2;
+    double* const fdst = a.fws ? a.fws + nx_b * a.fws_stride : nullptr;    // TASK_FACTOR served by this kernel
     static_for<0, NB>([&](auto Jc) {
       constexpr int J = decltype(Jc)::value;
       constexpr int NTJ = NB - J;
@@ -839,7 +844,11 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         const double2 f = ld_frag(tiles, kPhys[NB - 1][J][P], L);
         const double2 rv = ld_vec2(vr, 8 * P + 2 * L.t);
         pz = fma(f.x, rv.x, pz); pz2 = fma(f.y, rv.y, pz2);
+        // factor-once / predict-many: the retiring row leaves for the workspace of the grid kernel (-L[J][P]: see
+        // the NEGL note of gp64_kernel); every lane moves the 16-byte unit it owns, 512 contiguous bytes per tile
+        if (fdst) *reinterpret_cast<double2*>(fdst + slot(J, P) * TILE + L.nat) = make_double2(-f.x, -f.y);
       });
+      if (fdst) *reinterpret_cast<double2*>(fdst + slot(J, J) * TILE + L.nat) = make_double2(t0, t1);
       const double wv = vr[8 * J + L.g] - red_t(pz + pz2);
       double q = t0 * __shfl_sync(FULL, wv, L.t * 8) + t1 * __shfl_sync(FULL, wv, L.t * 8 + 4);
       q = red_t(q);
@@ -847,10 +856,14 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       __syncwarp();
     });
     quad = red_g(red_t(quad));
+    if (fdst) {                                           // z = L^-1 r behind the tiles
+#pragma unroll
+      for (int i0 = 0; i0 < LD; i0 += 32) { const int i = i0 + lane; if (i < LD) fdst[NTF * TILE + i] = vr[i]; }
+    }
     if (lane == 0) {
       a.info[io] = bad;
       const double logdet = log(lp_m) + (double)lp_e * LN2;
-      a.ll[io] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+      if (a.ll) a.ll[io] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
     }
   }
 }
@@ -890,7 +903,11 @@ template <int DIM, int TASK, int NB>
 int launch64(const SmallArgs& a, cudaStream_t stream) {
   static int compact = -1;                                // CGP_LL_COMPACT=0 falls back to the 36-slot kernel
   if (compact < 0) { const char* e = getenv("CGP_LL_COMPACT"); compact = (e && !atoi(e)) ? 0 : 1; }
-  if (TASK == TASK_LL && compact) return launch64_ll<DIM, NB>(a, stream);
+  // TASK_FACTOR = the compact likelihood kernel with a workspace: rows are written out as they retire, so the factor
+  // kernel keeps the 16 warps per SM of the likelihood kernel instead of 11 (CGP_FACTOR_COMPACT=0: the 36-slot kernel)
+  static int fcompact = -1;
+  if (fcompact < 0) { const char* e = getenv("CGP_FACTOR_COMPACT"); fcompact = (e && !atoi(e)) ? 0 : 1; }
+  if ((TASK == TASK_LL && compact) || (TASK == TASK_FACTOR && fcompact)) return launch64_ll<DIM, NB>(a, stream);
   auto kern = gp64_kernel<DIM, TASK, NB>;
   const size_t smem = ((size_t)(NB * (NB + 1) / 2) * TILE + (size_t)(DIM + 1 + n_vec64(TASK)) * 8 * NB) * sizeof(double);
   static int sm_counts[16] = {0}, per_sms[16] = {0};   // per device of this process

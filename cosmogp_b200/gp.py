@@ -479,18 +479,46 @@ class Gaussian_process:
             self.get_covariance_matrix()
 
     def get_covariance_matrix(self):
-        """covariance_matrix[sn] = K(grid,grid)+nugget^2 - H K^-1 H^T (:340-361), on access."""
+        """covariance_matrix[sn] = K(grid,grid)+nugget^2 - H K^-1 H^T (:340-361).  Objects of <= 64 points: written in
+        bulk by cgp_covariance_batched_dev, a chunk of objects (<= 256 MB of matrices) per launch pair, when first
+        read; larger objects one by one through the blocked large-object path."""
         from . import dense
         hyp, nug = np.array(self.hyperparameters, dtype=float), float(self.nugget)
+        own = self.as_the_same_time
+        grid = None if own else np.ascontiguousarray(self.new_binning, dtype=np.float64)
 
         def make(i):
             o0, o1 = self._off[i], self._off[i + 1]
-            grid = self._x_flat[o0:o1] if self.as_the_same_time else np.ascontiguousarray(self.new_binning, dtype=np.float64)
+            g = self._x_flat[o0:o1] if own else grid
             return dense.predictive_covariance(
                 self._x_flat[o0:o1], None if self._ye_flat is None else self._ye_flat[o0:o1],
-                grid, hyp, nug, self._dim, self.flags)
+                g, hyp, nug, self._dim, self.flags)
 
-        self.covariance_matrix = _LazyMatrices(self.N_sn, make)
+        sizes = np.diff(self._off)
+        if self._devices is not None or len(sizes) == 0 or int(sizes.max()) > 64:
+            self.covariance_matrix = _LazyMatrices(self.N_sn, make)
+            return
+        per = (sizes.astype(np.int64) ** 2 if own else np.full(self.N_sn, len(grid) ** 2, dtype=np.int64)) * 8
+        bounds = [0]                                         # chunks of objects with <= 256 MB of matrices
+        acc = 0
+        for i in range(self.N_sn):
+            if acc and acc + per[i] > (256 << 20):
+                bounds.append(i); acc = 0
+            acc += per[i]
+        bounds.append(self.N_sn)
+        cache = {}
+
+        def make_bulk(i):
+            c = int(np.searchsorted(bounds, i, side="right")) - 1
+            if c not in cache:
+                cache.clear()                                # one chunk of host matrices alive at a time
+                mats, info = self.batch.covariance(hyp, nug, grid, objects=(bounds[c], bounds[c + 1]), flags=self.flags)
+                if info.any():
+                    self._raise_if_bad(np.concatenate([np.zeros(bounds[c], dtype=info.dtype), info]))
+                cache[c] = mats
+            return cache[c][i - bounds[c]]
+
+        self.covariance_matrix = _LazyMatrices(self.N_sn, make_bulk)
 
 
 class gaussian_process(Gaussian_process):

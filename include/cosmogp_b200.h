@@ -223,6 +223,17 @@ int cgp_loo_batched_host(int64_t n_obj, const int64_t* off, int dim,
                          const double* hyp, double nugget, double floor, unsigned flags, int mode,
                          double* pred, double* pred_var, double* pull, double* resid, int* info);
 
+/* ---- covariance_matrix of every object at once: replaces the loop of get_covariance_matrix
+ *      (cosmogp/Gaussian_process.py:340-361).  cov[b] = K(grid,grid) + nugget^2 I - H K^-1 H^T, row-major M x M
+ *      blocks: at b * m_shared^2 for a shared grid, at coff[b] for per-object grids (then goff (device), goff_host
+ *      (the same offsets on the host) and coff (device, CSR of M_b^2) are all required).  Objects of <= 64 points.
+ *      NaN blocks where info != 0. */
+int cgp_covariance_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
+                               const double* x, const double* y_err,
+                               const double* hyp, double nugget, double floor, unsigned flags,
+                               const double* xnew, const int64_t* goff, const int64_t* goff_host, int64_t m_shared,
+                               double* cov, const int64_t* coff, int* info, void* stream);
+
 /* ---- matrices for the attribute surface (kernel_matrix, inv_kernel_matrix:
  *      Gaussian_process.py:256-267, 319-325).  moff[n_obj+1]: CSR into the outputs in
  *      doubles (object b is an N_b x N_b row-major block).  kmat / kinv may be NULL. */

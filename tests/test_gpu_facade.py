@@ -416,3 +416,44 @@ def test_large_objects_through_the_facade(cg):
     y0 = O.return_mean_1d(y1, x1, ym, tm)
     mo, vo = O.predict(y1, x1, [0.5, 3.0], 0.0, x1, ye1, y0, y0, full_cov=False)
     assert_close(g1.Prediction[0], mo, 1e-9, 1e-11); assert_close(g1.prediction_variance[0], vo, 1e-9, 1e-12)
+
+
+def test_bulk_covariance_writer(cg):
+    """covariance_matrix of many objects at once (cgp_covariance_batched_dev) against the reference fixture and the
+    oracle: shared grid, per-object epochs (new_binning=None), 1D and 2D."""
+    from conftest import golden
+    from oracle import gp_oracle as O
+    from cosmogp_b200.batch import DeviceBatch, pack_csr
+    g = golden("kat_1d")
+    gp = cg.gaussian_process(g["y"], g["x"], y_err=g["y_err"])
+    gp.hyperparameters = g["hyp"]; gp.nugget = float(g["nugget"])
+    gp.get_prediction(new_binning=g["grid"], svd_method=False)
+    assert_close(gp.covariance_matrix[0], g["cov"], 1e-9, 1e-12)
+    rng = np.random.default_rng(17)
+    sizes = rng.integers(3, 64, 300)
+    xs = [np.sort(rng.uniform(-10, 40, n)) for n in sizes]
+    ys = [rng.standard_normal(n) for n in sizes]; yes = [rng.uniform(0.1, 0.3, n) for n in sizes]
+    hyp, nug = [0.6, 2.5], 0.07
+    grid = np.linspace(-12, 42, 77)
+    gn = cg.gaussian_process_nobject(ys, xs, y_err=yes)
+    gn.hyperparameters = np.array(hyp); gn.nugget = nug
+    gn.get_prediction(new_binning=grid, COV=True, svd_method=False)
+    for i in (0, 150, 299):
+        _, co = O.predict(ys[i], xs[i], hyp, nug, grid, yes[i])
+        assert_close(gn.covariance_matrix[i], co, 1e-9, 1e-11)
+        assert_close(np.diag(gn.covariance_matrix[i]), gn.prediction_variance[i], 1e-9, 1e-12)
+    gn.get_prediction(COV=True, svd_method=False)                      # every object on its own epochs
+    for i in (3, 200):
+        _, co = O.predict(ys[i], xs[i], hyp, nug, xs[i], yes[i])
+        assert gn.covariance_matrix[i].shape == (sizes[i], sizes[i])
+        assert_close(gn.covariance_matrix[i], co, 1e-9, 1e-11)
+    # all matrices of a batch in one call, 2D objects
+    x2 = [rng.uniform(-50, 50, (n, 2)) for n in sizes[:40]]
+    xf, off = pack_csr(x2, 2); yf, _ = pack_csr(ys[:40], 1); ef, _ = pack_csr(yes[:40], 1)
+    b2 = DeviceBatch(xf, yf, off, y_err=ef, dim=2)
+    h2 = [1.1, 20.0, 15.0, 30.0]; g2 = rng.uniform(-50, 50, (33, 2))
+    mats, info = b2.covariance(h2, 0.05, g2)
+    assert mats.shape == (40, 33, 33) and not info.any()
+    for i in (0, 39):
+        _, co = O.predict(ys[i], x2[i], h2, 0.05, g2, yes[i], kind="2d")
+        assert_close(mats[i], co, 1e-9, 1e-11)

@@ -45,4 +45,16 @@ rel = lambda a, b: float(((a - b).abs() / b.abs()).max())
 res["fused_vs_split"] = [rel(f[0], s[0]), rel(f[1], s[1]), rel(f[2], s[2])]
 res["fused_ll_vs_ll_kernel"] = rel(f[0], ll0)
 res["objects"] = B
+# never report a time for wrong numbers: the first objects against the numpy oracle (checker)
+from oracle import gp_oracle as O
+k = 16
+y0m = y0.reshape(B, bench.N_EPOCH)
+ll_o = O.ll_batched_1d(x[:k], y[:k], y0m[:k], ye[:k], HYP, NUG)
+mo, vo = O.predict_batched_1d(x[:k], y[:k], y0m[:k], ye[:k], HYP, NUG, grid, tmpl[None, :] + d[:k, None])
+npy = lambda t, n: t[:n].cpu().numpy()
+res["parity_vs_oracle"] = max(float(np.max(np.abs(npy(f[0], k) - ll_o) / np.abs(ll_o))),
+                              float(np.max(np.abs(npy(f[1], k * bench.M_GRID).reshape(k, -1) - mo) / np.abs(mo))),
+                              float(np.max(np.abs(npy(f[2], k * bench.M_GRID).reshape(k, -1) - vo) / np.abs(vo))),
+                              float(np.max(np.abs(npy(ll0, k) - ll_o) / np.abs(ll_o))))
+assert res["parity_vs_oracle"] < 1e-9, res
 print(json.dumps(res))
