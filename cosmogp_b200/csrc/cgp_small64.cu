@@ -150,23 +150,36 @@ static unsigned long long* next_ticket(cudaStream_t stream) {
 }
 
 constexpr int n_vec64(int task) { return task == TASK_LOO ? 6 : 1; }
+// Warps per CTA that share one staged factor in the grid kernels (see WPC in gp64_kernel).  Measured at C2 with 2: 16 warps
+// per SM on 8 factors, but 7 passes split 4 + 3 between the two warps, two CTA barriers per object and 128-register
+// spills: grid kernel 2.13 -> 2.42 ms.  Kept at 1 (CGP64_GRID_WPC=2 at compile time selects the shared form; tested).
+#ifndef CGP64_GRID_WPC
+#define CGP64_GRID_WPC 1
+#endif
+__host__ __device__ constexpr int warps_per_cta(int task) { return (task == TASK_PREDICT_F || task == TASK_PREDICT_FU) ? CGP64_GRID_WPC : 1; }
 
 // Registers are allocated per SM sub-partition (16 K each): 3 warps per partition need <= 168
 // registers per thread (grid phase: 64 accumulators + 32 fragments), 4 warps <= 128 (factorisation,
 // pulls: shared memory allows 16+ objects per SM below 56 points); hence the minimum-blocks bounds.
 template <int DIM, int TASK, int NB>
-__global__ void __launch_bounds__(32, (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU || TASK == TASK_PREDICT_U) ? 12 : 16)
+__global__ void __launch_bounds__(32 * warps_per_cta(TASK), warps_per_cta(TASK) > 1 ? 16 / warps_per_cta(TASK) :
+                                  (TASK == TASK_PREDICT || TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU || TASK == TASK_PREDICT_U) ? 12 : 16)
 gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x;
+  // WPC warps per CTA share ONE object: the grid kernels (factor staged from the workspace) run two warps on the
+  // same shared-memory tiles, alternating over the passes of the grid -- 16 warps per SM on 8 staged factors where one
+  // warp per object was limited to 11 by shared memory (the grid phase needs < 128 registers since the forward
+  // substitution keeps no separate cross-covariance fragments).  Every other task: one warp, one object.
+  constexpr int WPC = warps_per_cta(TASK);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Lane L(lane);
   Cov cov = a.cov;
   constexpr int LD = 8 * NB;
   constexpr int NT = NB * (NB + 1) / 2;
   double* tiles = smem;
-  double* px = tiles + NT * TILE;          // DIM * LD
+  double* px = tiles + NT * TILE + warp * (DIM + 1) * LD;     // DIM * LD, one set per warp (the uniform-grid anchors live here)
   double* noise = px + DIM * LD;
-  double* vr = noise + LD;                 // r (LL: becomes z)
+  double* vr = tiles + NT * TILE + WPC * (DIM + 1) * LD;      // r (becomes z); shared by the warps of the CTA
   constexpr bool PF = TASK == TASK_PREDICT_F || TASK == TASK_PREDICT_FU;      // predict from a stored factor
   constexpr bool UNI = TASK == TASK_PREDICT_FU || TASK == TASK_PREDICT_U;      // ... on a uniformly spaced shared grid
   constexpr bool FUSED = TASK == TASK_PREDICT || TASK == TASK_PREDICT_U;       // factorise and predict in one pass (no workspace)
@@ -189,13 +202,14 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   // factor workspace of one object: NT tiles in fragment order followed by alpha (LD doubles)
   constexpr int WS = NT * TILE + LD;
   __shared__ __align__(8) unsigned long long s_mbar;       // TMA completion barrier (TASK_PREDICT_F)
+  __shared__ long long s_tk[2];                            // WPC > 1: the ticket drawn by thread 0, double buffered
   unsigned mbar_parity = 0;
   if (PF) {
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(&s_mbar)));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    if (WPC > 1) __syncthreads(); else __syncwarp();
   }
 
   // Dynamic work distribution: 11 one-warp CTAs per SM land 3/3/3/2 on the four sub-partitions,
@@ -236,11 +250,21 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     uni_2hd = 2.0 * cov.h00 * uni_delta;
   }
   int64_t w = blockIdx.x, w_nxt = (int64_t)blockIdx.x + gridDim.x, t_next = 0;
+  int it = 0;
+  // next work item: one warp per CTA shuffles it from lane 0; several warps meet at a barrier (which also says that
+  // every warp is done with the staged factor of the current object) and read it from shared memory
+  auto advance = [&]() -> int64_t {
+    if (WPC > 1) { __syncthreads(); return s_tk[(it++) & 1]; }
+    return __shfl_sync(FULL, t_next, 0);
+  };
   Next nx;
   fetch(w, nx);
-  for (;; w = w_nxt, w_nxt = __shfl_sync(FULL, t_next, 0)) {
+  for (;; w = w_nxt, w_nxt = advance()) {
     if (w >= n_work) break;
-    if (lane == 0) t_next = (int64_t)atomicAdd(ticket, 1ULL) + 2 * (int64_t)gridDim.x;
+    if (threadIdx.x == 0) {
+      t_next = (int64_t)atomicAdd(ticket, 1ULL) + 2 * (int64_t)gridDim.x;
+      if (WPC > 1) s_tk[it & 1] = t_next;
+    }
     const int64_t oi = w / split;
     const int part = (int)(w - oi * split);
     const int64_t b = a.order ? a.order[oi] : oi;
@@ -259,8 +283,10 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
       if (i < LD) {
         px[i] = nx.x[k];
         if (DIM == 2) px[LD + i] = nx.y2[k];
-        noise[i] = nx.ye[k] * nx.ye[k] + cov.noise_const;
-        vr[i] = nx.r[k]; rsum += nx.r[k];
+        if (!PF) {                                         // PF: z arrives by TMA into vr, nothing else is staged
+          noise[i] = nx.ye[k] * nx.ye[k] + cov.noise_const;
+          vr[i] = nx.r[k]; rsum += nx.r[k];
+        }
       }
     }
     double xo[NR];                                       // UNI: this lane owns columns lane, lane+32
@@ -274,7 +300,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     if (PF) {
       // L^-1 tiles + alpha of this object: one TMA bulk copy global -> shared, completion on an mbarrier
       const unsigned mb = (unsigned)__cvta_generic_to_shared(&s_mbar);
-      if (lane == 0) {
+      if (threadIdx.x == 0) {
         const unsigned bytes = NT * TILE * 8;
         const double* src = a.fws + b * a.fws_stride;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the buffer are done
@@ -587,8 +613,9 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           pny0[u] = (lv && a.new_y0) ? (a.new_y0_diff ? a.new_y0[m] + a.new_y0_diff[b] : a.new_y0[out0 + m]) : 0.0;
         }
       };
-      grid_fetch((int64_t)part * 2);
-      for (int64_t rb = (int64_t)part * 2; rb < n_rb; rb += (int64_t)split * 2) {
+      const int64_t rb0 = (int64_t)(part * WPC + warp) * 2, rbs = (int64_t)split * WPC * 2;   // the warps of a CTA alternate over the passes
+      grid_fetch(rb0);
+      for (int64_t rb = rb0; rb < n_rb; rb += rbs) {
         int64_t mi[2]; bool live[2]; double gx[2], gy[2], ny0[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -596,7 +623,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           live[u] = mi[u] < m_pts;
           gx[u] = pgx[u]; gy[u] = pgy[u]; ny0[u] = pny0[u];
         }
-        grid_fetch(rb + (int64_t)split * 2);               // next pair's coordinates, behind this pair's math
+        grid_fetch(rb + rbs);                              // next pair's coordinates, behind this pair's math
         // cross-covariance fragments (no amplitude), generated straight into the accumulators of the forward
         // substitution: lane (g,t) holds H[grid row g][columns 8P+2t, 8P+2t+1] = the start value of W_P
         double acc0[2][NB], acc1[2][NB];
@@ -909,7 +936,8 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
   if (fcompact < 0) { const char* e = getenv("CGP_FACTOR_COMPACT"); fcompact = (e && !atoi(e)) ? 0 : 1; }
   if ((TASK == TASK_LL && compact) || (TASK == TASK_FACTOR && fcompact)) return launch64_ll<DIM, NB>(a, stream);
   auto kern = gp64_kernel<DIM, TASK, NB>;
-  const size_t smem = ((size_t)(NB * (NB + 1) / 2) * TILE + (size_t)(DIM + 1 + n_vec64(TASK)) * 8 * NB) * sizeof(double);
+  constexpr int WPC = warps_per_cta(TASK);
+  const size_t smem = ((size_t)(NB * (NB + 1) / 2) * TILE + (size_t)(WPC * (DIM + 1) + n_vec64(TASK)) * 8 * NB) * sizeof(double);
   static int sm_counts[16] = {0}, per_sms[16] = {0};   // per device of this process
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return (int)cudaErrorInvalidDevice;
@@ -919,7 +947,7 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WPC, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) return (int)cudaErrorInvalidConfiguration;
     per_sm = occ;
@@ -932,7 +960,7 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
   if (grid < 1) return 0;
   unsigned long long* ticket = next_ticket(stream);
   if (!ticket) return (int)cudaErrorMemoryAllocation;
-  kern<<<(unsigned)grid, 32, smem, stream>>>(a, ticket);
+  kern<<<(unsigned)grid, 32 * WPC, smem, stream>>>(a, ticket);
   count_launch();
   return (int)cudaGetLastError();
 }
