@@ -429,6 +429,9 @@ def main():
     # the likelihood evaluation alone, as the optimiser drives it: the compact LL kernel (its own factorisation, rows retired)
     # + the device reduction + 16 bytes back; kernel time by CUDA events, wall time of the whole call
     batch.log_likelihood_total(HYP, NUGGET)
+    for _ in range(3):
+        batch.ll_dev(HYP, NUGGET)
+    torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_ll = max(5, args.steps)
     k0.record()
