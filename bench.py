@@ -532,8 +532,8 @@ def main():
                               "what": "64 MB pinned copies in both directions on every rank at the same time, measured in this run: "
                                       "the step cannot be faster than its larger direction at this rate"}},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,PREDICT_FU,8>: predictive mean+variance on the (uniform) grid "
-                     "from the TMA-staged factor (FP64 tensor pipe, DMMA.8x8x4)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "gp64_kernel<1,PREDICT_FU,8>: predictive mean+variance on the (uniform) grid by block forward "
+                     "substitution against the TMA-staged Cholesky factor (FP64 tensor pipe, DMMA.8x8x4)", "achieved": achieved,
                      "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma, "traffic": traffic,
                      "traffic_source": traffic_src,
                      "peak_source": "FP64 DMMA m8n8k4 ceiling measured in this run (cgp_fp64_peak); MEASURED_PEAKS.json "
@@ -542,7 +542,7 @@ def main():
                      "factor_kernel": {"ms_per_launch": fa_ms, "flop_per_object": fl_factor,
                                        "achieved": fl_factor * B / (fa_ms * 1e-3) * 1e-12,
                                        "frac": fl_factor * B / (fa_ms * 1e-3) * 1e-12 / peak_dmma,
-                                       "what": "covariance + Cholesky + L^-1 + alpha + log-likelihood, spilled for the grid kernel"},
+                                       "what": "covariance + Cholesky + z = L^-1 r + log-likelihood; block rows written to the grid kernel's workspace as they retire"},
                      "whole_step": {"flop_per_object": fl_step, "achieved": fl_step * B * args.steps / (total_ms * 1e-3) * 1e-12,
                                     "frac": fl_step * B * args.steps / (total_ms * 1e-3) * 1e-12 / peak_dmma}},
         "ll_evaluation": {"kernel_ms": ll_ms, "wall_ms": ll_wall_ms, "flop_per_object": flops_ll(N_EPOCH),
