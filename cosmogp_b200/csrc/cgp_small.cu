@@ -11,16 +11,18 @@
 // rank-8 updates, triangular solves, L^-1 and L^-1-applications all run on the FP64
 // tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), and consumed in place.
 //
-// Tile storage ("fragment order"): element (r, c) of an 8x8 tile lives at
-//   (r*4 + (c&3))*2 + (c>>2)
-// so that lane (g = lane/4, t = lane%4) fetches both k-halves of its DMMA A/B fragment
-// {tile[g][t], tile[g][4+t]} with ONE conflict-free 16-byte load at lane*2, and the
-// transposed fragment {tile[t][g], tile[4+t][g]} with two conflict-free 8-byte loads.
-// With the m8n8k4 layouts (A[g][t], B[t][g], C[g][2t..2t+1]) this gives, with no
-// data movement, all three products the algorithm needs:
-//   X*Y^T (frag, frag)   X*Y (frag, fragT)   X^T*Y (fragT, fragT).
+// Tile storage (the layout of cgp_small64.cu, see its header): element (r, c) of an 8x8 tile lives in 16-byte unit
+//   rho(r)*4 + ((c>>1) ^ sigma(r)), half c&1,   rho(r) = r ^ ((r>>1)&1), sigma(r) = (r>>1)&2
+// so that lane (g = lane/4, t = lane%4) finds its DMMA accumulator pair {tile[g][2t], tile[g][2t+1]} -- which is also its
+// operand of both k-halves of a product X*Y^T (the two DMMAs sum over the even and the odd k) -- in ONE conflict-free
+// 16-byte unit, and the transposed fragment {tile[2t][g], tile[2t+1][g]} with two conflict-free 8-byte loads.  With the
+// m8n8k4 layouts (A[g][k], B[k][g], C[g][2t..2t+1]) this gives all three products the algorithm needs,
+//   X*Y^T (frag, frag)   X*Y (frag, fragT)   X^T*Y (fragT, fragT),
+// and lets a tile that was just accumulated feed the next DMMA straight from its registers.
 #include "cgp_internal.h"
 #include "cgp_math.cuh"
+
+#pragma nv_diag_suppress 128      // TASK_PREDICT leaves the object loop before the L^-1 phase: "loop is not reachable" there
 
 #include <math.h>
 #include <stdio.h>
@@ -39,17 +41,18 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 __device__ __forceinline__ int slot(int i, int j) { return ((i * (i + 1)) >> 1) + j; }   // i >= j
-__host__ __device__ __forceinline__ int frag_off(int r, int c) { return ((r * 4 + (c & 3)) << 1) + (c >> 2); }
+__host__ __device__ __forceinline__ int frag_off(int r, int c) {
+  const int rho = r ^ ((r >> 1) & 1), sig = (r >> 1) & 2;
+  return ((rho * 4 + ((c >> 1) ^ sig)) << 1) + (c & 1);
+}
 
 struct Lane {
   int g, t;
-  int fr;          // lane*2: this lane's fragment pair
-  int st0, st1;    // where accumulator elements (g,2t), (g,2t+1) go
-  int tr0, tr1;    // transposed fragment: (t,g), (4+t,g)
+  int fr;          // this lane's 16-byte unit: elements (g,2t), (g,2t+1) = accumulator pair = operand fragment
+  int tr0, tr1;    // transposed fragment: (2t,g), (2t+1,g)
   __device__ explicit Lane(int lane) {
-    g = lane >> 2; t = lane & 3; fr = lane << 1;
-    st0 = frag_off(g, 2 * t); st1 = frag_off(g, 2 * t + 1);
-    tr0 = frag_off(t, g); tr1 = frag_off(4 + t, g);
+    g = lane >> 2; t = lane & 3; fr = frag_off(g, 2 * t);
+    tr0 = frag_off(2 * t, g); tr1 = frag_off(2 * t + 1, g);
   }
 };
 
@@ -61,8 +64,7 @@ __device__ __forceinline__ double2 ld_fragT(const double* tiles, int s, const La
   return make_double2(p[L.tr0], p[L.tr1]);
 }
 __device__ __forceinline__ void st_acc(double* tiles, int s, const Lane& L, double c0, double c1) {
-  double* p = tiles + s * TILE;
-  p[L.st0] = c0; p[L.st1] = c1;
+  *reinterpret_cast<double2*>(tiles + s * TILE + L.fr) = make_double2(c0, c1);
 }
 __device__ __forceinline__ double red_t(double v) {     // sum over the 4 lanes of a row group
   v += __shfl_xor_sync(FULL, v, 1); v += __shfl_xor_sync(FULL, v, 2); return v;
@@ -166,6 +168,10 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
   Cov cov = a.cov;
   constexpr int NT = WARPS * 32;
   constexpr int KMAX = (NB_MAX - 1 + WARPS - 1) / WARPS;   // L^-1 row: tiles per warp
+  // Prediction by block forward substitution (no L^-1, see below) up to 128 points.  Beyond, one object fills the shared
+  // memory of an SM (one warp per sub-partition) and the 28 dependent steps of the substitution are exposed: there the
+  // product with an explicit L^-1 (28 independent accumulator chains per grid block) stays faster (N = 224: 14 vs 21 ms).
+  constexpr bool FWD = (TASK == TASK_PREDICT) && NB_MAX <= 16;
 
   const int ld = 8 * nbm;
   double* tiles = smem;                                   // nbm(nbm+1)/2 tiles
@@ -276,8 +282,11 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
         dmma(d0, d1, fc.x, ft.x); dmma(e0, e1, fc.y, ft.y);
         dmma(f0, f1, fe.x, ft.x); dmma(g0, g1, fe.y, ft.y);
         __syncwarp();
-        st_acc(tiles, slot(I, J), L, d0 + e0, d1 + e1);
-        if (two) st_acc(tiles, slot(I2, J), L, f0 + g0, f1 + g1);
+        // prediction keeps -L below the diagonal: the forward substitution of the grid phase then accumulates
+        // h + sum V_P (-L[J][P])^T directly (the rank updates of later columns do not notice the sign)
+        constexpr double sgn = FWD ? -1.0 : 1.0;
+        st_acc(tiles, slot(I, J), L, sgn * (d0 + e0), sgn * (d1 + e1));
+        if (two) st_acc(tiles, slot(I2, J), L, sgn * (f0 + g0), sgn * (f1 + g1));
       }
       cta_sync<WARPS>();
     }
@@ -291,11 +300,11 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
           const double* tj = tiles + slot(J, 0) * TILE + L.fr;
           for (int P = 0; P < J; ++P) {
             const double2 f = *reinterpret_cast<const double2*>(tj + P * TILE);
-            p = fma(f.x, vr[8 * P + L.t], p); p2 = fma(f.y, vr[8 * P + 4 + L.t], p2);
+            p = fma(f.x, vr[8 * P + 2 * L.t], p); p2 = fma(f.y, vr[8 * P + 2 * L.t + 1], p2);
           }
           const double wv = vr[8 * J + L.g] - red_t(p + p2);
           const double2 f = *reinterpret_cast<const double2*>(tj + J * TILE);
-          double q = f.x * __shfl_sync(FULL, wv, L.t * 4) + f.y * __shfl_sync(FULL, wv, (4 + L.t) * 4);
+          double q = f.x * __shfl_sync(FULL, wv, L.t * 8) + f.y * __shfl_sync(FULL, wv, L.t * 8 + 4);
           q = red_t(q);
           if (L.t == 0) { vr[8 * J + L.g] = q; quad = fma(q, q, quad); }
           __syncwarp();
@@ -306,6 +315,88 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
           a.info[io] = bad;
           const double logdet = log(lp_m) + (double)lp_e * 0.693147180559945309417232;
           a.ll[io] = bad ? nan("") : -0.5 * (quad + logdet + n * LOG_2PI);
+        }
+      }
+      continue;
+    }
+
+    if (FWD) {
+      // ---------------- prediction without L^-1 (see cgp_small64.cu): z = L^-1 r by block forward substitution (warp 0),
+      // then per block of 8 grid points the same substitution for the cross-covariance rows ON THE TENSOR CORES:
+      // V_P = W_P T_P^T (operands: the accumulator registers and the T_P tile), W_J += V_P (-L[J][P])^T for J > P;
+      // mean = v . z + y0*, var = amp* - |v|^2.  h is kept WITHOUT its amplitude (applied once per grid point).
+      if (warp == 0) {
+        for (int J = 0; J < nb; ++J) {
+          double p = 0.0, p2 = 0.0;
+          const double* tj = tiles + slot(J, 0) * TILE + L.fr;
+          for (int P = 0; P < J; ++P) {
+            const double2 f = *reinterpret_cast<const double2*>(tj + P * TILE);
+            p = fma(f.x, vr[8 * P + 2 * L.t], p); p2 = fma(f.y, vr[8 * P + 2 * L.t + 1], p2);
+          }
+          const double wv = vr[8 * J + L.g] + red_t(p + p2);                 // the tiles hold -L
+          const double2 f = *reinterpret_cast<const double2*>(tj + J * TILE);
+          double q = f.x * __shfl_sync(FULL, wv, L.t * 8) + f.y * __shfl_sync(FULL, wv, L.t * 8 + 4);
+          q = red_t(q);
+          if (L.t == 0) vr[8 * J + L.g] = q;
+          __syncwarp();
+        }
+      }
+      cta_sync<WARPS>();
+      const int bad = s_bad;
+      if (tid == 0 && part == 0) a.info[b] = bad;
+      const int64_t g0 = a.goff ? a.goff[b] : 0;
+      const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
+      const int64_t out0 = a.goff ? g0 : b * a.m_shared;
+      const int64_t n_rb = (m_pts + 7) >> 3;
+      const double amp_star = cov.amp_auto + cov.nugget2;
+      for (int64_t rb = (int64_t)part * WARPS + warp; rb < n_rb; rb += (int64_t)split * WARPS) {
+        const int64_t mi = 8 * rb + L.g;
+        const bool live = mi < m_pts;
+        double gx = 0.0, gy = 0.0;
+        if (live) {
+          if (DIM == 1) gx = a.xnew[g0 + mi];
+          else { gx = a.xnew[2 * (g0 + mi)]; gy = a.xnew[2 * (g0 + mi) + 1]; }
+        }
+        double acc0[NB_MAX], acc1[NB_MAX];
+#pragma unroll
+        for (int P = 0; P < NB_MAX; ++P) {                // cross-covariance fragments = start values of W_P
+          acc0[P] = 0.0; acc1[P] = 0.0;
+          if (P < nb) {
+            const int c0 = 8 * P + 2 * L.t, c1 = c0 + 1;
+            if (live && c0 < n) acc0[P] = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c0], DIM == 2 ? px[ld + c0] : 0.0));
+            if (live && c1 < n) acc1[P] = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c1], DIM == 2 ? px[ld + c1] : 0.0));
+          }
+        }
+        double pm = 0.0, pm2 = 0.0, vv = 0.0, vv2 = 0.0;
+#pragma unroll
+        for (int P = 0; P < NB_MAX; ++P) {
+          if (P < nb) {
+            const double2 ft = ld_frag(tiles, slot(P, P), L);
+            double r0 = 0.0, r1 = 0.0, e0 = 0.0, e1 = 0.0;
+            dmma(r0, r1, acc0[P], ft.x); dmma(e0, e1, acc1[P], ft.y);
+            const double v0 = r0 + e0, v1 = r1 + e1;
+            acc0[P] = v0; acc1[P] = v1;
+            pm = fma(v0, vr[8 * P + 2 * L.t], pm); pm2 = fma(v1, vr[8 * P + 2 * L.t + 1], pm2);
+            vv = fma(v0, v0, vv); vv2 = fma(v1, v1, vv2);
+            if (a.vout && live)                           // bulk covariance writer (cgp_covariance_batched_dev)
+              *reinterpret_cast<double2*>(a.vout + (out0 + mi) * ld + 8 * P + 2 * L.t) = make_double2(v0, v1);
+#pragma unroll
+            for (int J = P + 1; J < NB_MAX; ++J) {        // compile-time triangle: no wasted DMMA
+              if (J < nb) {
+                const double2 fb = ld_frag(tiles, slot(J, P), L);
+                dmma(acc0[J], acc1[J], v0, fb.x); dmma(acc0[J], acc1[J], v1, fb.y);
+              }
+            }
+          }
+        }
+        pm = red_t(pm + pm2); vv = red_t(vv + vv2);
+        if (live && L.t == 0) {
+          const double m0 = !a.new_y0 ? 0.0 : (a.new_y0_diff ? a.new_y0[mi] + a.new_y0_diff[b] : a.new_y0[out0 + mi]);
+          double mean = fma(cov.amp_cross, pm, m0);
+          double var = fma(-cov.amp_cross * cov.amp_cross, vv, amp_star);
+          if (bad) { mean = nan(""); var = mean; }
+          a.mean[out0 + mi] = mean;
+          if (a.var) a.var[out0 + mi] = var;
         }
       }
       continue;
@@ -369,7 +460,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
             if (q % WARPS != warp) continue;
             const double* tp = tiles + slot(I, J <= I ? J : 0) * TILE;
             const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
-            double c0 = (J <= I) ? tp[L.st0] : 0.0, c1 = (J <= I) ? tp[L.st1] : 0.0;
+            double c0 = (J <= I) ? tp[L.fr] : 0.0, c1 = (J <= I) ? tp[L.fr + 1] : 0.0;
             if (bad) { c0 = nan(""); c1 = c0; }
             if (gi < n && cj < n) a.linv[mo + (int64_t)gi * mld + cj] = c0;
             if (gi < n && cj + 1 < n) a.linv[mo + (int64_t)gi * mld + cj + 1] = c1;
@@ -404,7 +495,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
       const double* ti = tiles + slot(I, 0) * TILE + L.fr;
       for (int J = 0; J <= I; ++J) {
         const double2 f = *reinterpret_cast<const double2*>(ti + J * TILE);
-        p = fma(f.x, vr[8 * J + L.t], p); p2 = fma(f.y, vr[8 * J + 4 + L.t], p2);
+        p = fma(f.x, vr[8 * J + 2 * L.t], p); p2 = fma(f.y, vr[8 * J + 2 * L.t + 1], p2);
         if (want_u) {                                     // padded columns multiply exact zeros of L^-1
           p1 += f.x; p1 += f.y;
         }
@@ -428,13 +519,13 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
         }
       }
       pa0 = red_g(pa0); pa1 = red_g(pa1);
-      if (L.g == 0) { va[8 * J + L.t] = pa0; va[8 * J + 4 + L.t] = pa1; }
+      if (L.g == 0) { va[8 * J + 2 * L.t] = pa0; va[8 * J + 2 * L.t + 1] = pa1; }
       if (TASK == TASK_LOO) {
         pd0 = red_g(pd0); pd1 = red_g(pd1);
-        if (L.g == 0) { vd[8 * J + L.t] = pd0; vd[8 * J + 4 + L.t] = pd1; }
+        if (L.g == 0) { vd[8 * J + 2 * L.t] = pd0; vd[8 * J + 2 * L.t + 1] = pd1; }
         if (want_u) {
           pu0 = red_g(pu0); pu1 = red_g(pu1);
-          if (L.g == 0) { vu[8 * J + L.t] = pu0; vu[8 * J + 4 + L.t] = pu1; }
+          if (L.g == 0) { vu[8 * J + 2 * L.t] = pu0; vu[8 * J + 2 * L.t + 1] = pu1; }
         }
       }
     }
@@ -470,8 +561,8 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
     }
 
     if (TASK == TASK_PREDICT) {
-      // ---------------- grid points in blocks of 8: v = L^-1 h, mean = h.alpha + y0*, var = amp* - |v|^2.
-      // h is kept WITHOUT its amplitude (applied once per grid point at the end).
+      // ---------------- N > 128: grid points in blocks of 8 against the explicit L^-1: v = L^-1 h, mean = h.alpha + y0*,
+      // var = amp* - |v|^2.  h is kept WITHOUT its amplitude (applied once per grid point at the end).
       const int64_t g0 = a.goff ? a.goff[b] : 0;
       const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
       const int64_t out0 = a.goff ? g0 : b * a.m_shared;
@@ -492,7 +583,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
 #pragma unroll
         for (int P = 0; P < NB_MAX; ++P) {
           if (P < nb) {
-            const int c0 = 8 * P + L.t, c1 = c0 + 4;
+            const int c0 = 8 * P + 2 * L.t, c1 = c0 + 1;
             double h0 = 0.0, h1 = 0.0;                    // A fragment of the cross-covariance block
             if (live && c0 < n) h0 = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c0], DIM == 2 ? px[ld + c0] : 0.0));
             if (live && c1 < n) h1 = cgp_exp(rbf_arg<DIM>(cov, gx, gy, px[c1], DIM == 2 ? px[ld + c1] : 0.0));
@@ -508,7 +599,11 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
         }
         double vv = 0.0, vv2 = 0.0;
 #pragma unroll
-        for (int J = 0; J < NB_MAX; ++J) { vv = fma(acc0[J], acc0[J], vv); vv2 = fma(acc1[J], acc1[J], vv2); }
+        for (int J = 0; J < NB_MAX; ++J) {
+          vv = fma(acc0[J], acc0[J], vv); vv2 = fma(acc1[J], acc1[J], vv2);
+          if (a.vout && live && J < nb)
+            *reinterpret_cast<double2*>(a.vout + (out0 + mi) * ld + 8 * J + 2 * L.t) = make_double2(acc0[J], acc1[J]);
+        }
         pm = red_t(pm + pm2); vv = red_t(vv + vv2);
         if (live && L.t == 0) {
           const double m0 = !a.new_y0 ? 0.0 : (a.new_y0_diff ? a.new_y0[mi] + a.new_y0_diff[b] : a.new_y0[out0 + mi]);
