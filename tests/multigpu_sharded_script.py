@@ -26,5 +26,28 @@ if rank == 0:
     print("ranges", gp.local_range, "hyp", gp.hyperparameters, "rel diff hyp %.2e  max diff pred %.2e  shape %s" % (dh, dp, pred.shape))
     assert pred.shape == (301, 64) and dh < 1e-6 and dp < 1e-6
     print("sharded facade ok")
+# a batch smaller than the number of ranks: the last rank owns the single object, the others an EMPTY shard; every rank must
+# still take part in the exchanges (likelihood total, gather) and end with the same numbers
+g1 = cg.gaussian_process_nobject.sharded(ys[:1], xs[:1], y_err=yes[:1])
+g1.compute_log_likelihood([0.5, 2.0], svd_method=False)
+g1.hyperparameters = np.array([0.5, 2.0])
+g1.get_prediction(new_binning=grid, COV='diag')
+p1 = g1.gather(g1.Prediction)
+root_only = g1.gather(g1.Prediction, root=0)
+assert (root_only is None) == (rank != 0)
+r1 = cg.gaussian_process_nobject(ys[:1], xs[:1], y_err=yes[:1])
+r1.compute_log_likelihood([0.5, 2.0], svd_method=False)
+r1.hyperparameters = np.array([0.5, 2.0]); r1.get_prediction(new_binning=grid, COV='diag')
+assert abs(g1.log_likelihood[0] - r1.log_likelihood[0]) < 1e-12 * abs(r1.log_likelihood[0]), (g1.log_likelihood, r1.log_likelihood)
+assert np.array(p1).shape == (1, 64) and np.max(np.abs(np.array(p1) - np.array(r1.Prediction))) < 1e-12
+# objects beyond the shared-memory path on one rank only: every rank must take the large-object branch (global sizes)
+big = [np.sort(rng.uniform(0, 100, 300)), np.sort(rng.uniform(0, 100, 40))]
+yb = [np.sin(b / 5.0) for b in big]; eb = [np.full(len(b), 0.2) for b in big]
+gl = cg.gaussian_process_nobject.sharded(yb, big, y_err=eb)
+gl.compute_log_likelihood([0.7, 3.0], svd_method=False)
+rl = cg.gaussian_process_nobject(yb, big, y_err=eb); rl.compute_log_likelihood([0.7, 3.0], svd_method=False)
+assert abs(gl.log_likelihood[0] - rl.log_likelihood[0]) < 1e-10 * abs(rl.log_likelihood[0]), (gl.log_likelihood, rl.log_likelihood)
+if rank == 0:
+    print("empty shard and mixed large/small shards ok", g1.local_range, gl.local_range)
 dist.barrier()
 dist.destroy_process_group()

@@ -19,4 +19,4 @@ def test_sharded_facade_two_ranks():
            "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(here, "multigpu_sharded_script.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "sharded facade ok" in out.stdout
+    assert "sharded facade ok" in out.stdout and "empty shard and mixed large/small shards ok" in out.stdout
