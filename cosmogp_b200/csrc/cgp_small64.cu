@@ -16,13 +16,15 @@
 //     solve and the triangular inverse need no shared-memory round trip);
 //   * the transposed fragment (elements (2t,g), (2t+1,g)) is two conflict-free 8-byte loads.
 // Phases:
-//   K   all covariance tiles generated up front, 8 independent exp chains per lane in flight
-//   C   column J: every tile of the column accumulates its rank-8J update at once
-//       (2 (NB-J) independent DMMA chains), one parked-K subtraction, in-register diagonal
-//       factorisation, panel solve by DMMA
-//   S   LL: block forward substitution;  or  L^-1 by rows (NB-1 independent chains)
-//   P   predict: TWO blocks of 8 grid points per pass, all 4 NB cross-covariance fragments
-//       generated first, then 4 NB(NB+1)/2 DMMAs on 4 NB independent accumulators
+//   K   covariance tiles: generated up front, 8 independent exp chains per lane in flight (gp64_kernel), or column by
+//       column right where they are consumed (gp64_ll_kernel, whose rows retire and free their slots)
+//   C   column J: every tile of the column accumulates its rank-8J update at once (2 (NB-J) independent DMMA
+//       chains), in-register diagonal factorisation (T_J = L_JJ^-1), panel solve by DMMA from registers,
+//       z_J = T_J (r_J - sum L[J][P] z_P) behind the next column
+//   I   pulls only: L^-1 by rows (held transposed while it is built), column norms, alpha
+//   P   prediction: TWO blocks of 8 grid points per pass; the 4 NB cross-covariance fragments are generated into the
+//       accumulators, then L v = h is solved by block forward substitution on the tensor cores (4 NB(NB+1)/2 DMMAs),
+//       mean = v . z, var = amp* - |v|^2 -- no L^-1, no alpha
 // Objects with fewer than NB blocks are padded with identity rows (exact, just wasteful);
 // per-object n masks the covariance entries.  Reference: see cgp_small.cu header.
 #include <atomic>
@@ -686,9 +688,8 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           const double2 zz = ld_vec2(va, 8 * P + 2 * L.t);
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            double r0 = 0.0, r1 = 0.0, e0 = 0.0, e1 = 0.0;
-            dmma(r0, r1, acc0[u][P], ft.x); dmma(e0, e1, acc1[u][P], ft.y);
-            const double v0 = r0 + e0, v1 = r1 + e1;
+            double v0 = 0.0, v1 = 0.0;
+            dmma(v0, v1, acc0[u][P], ft.x); dmma(v0, v1, acc1[u][P], ft.y);
             acc0[u][P] = v0; acc1[u][P] = v1;
             if (TASK == TASK_PREDICT && a.vout && live[u])      // bulk covariance writer: keep v (16 bytes per lane, 64-byte rows per quad)
               *reinterpret_cast<double2*>(a.vout + (out0 + mi[u]) * LD + 8 * P + 2 * L.t) = make_double2(v0, v1);
