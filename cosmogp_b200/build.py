@@ -36,10 +36,11 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     procs = []
-    units = [(src, [], src.replace(".cu", ".o")) for src in SOURCES]
+    extra = os.environ.get("CGP_BUILD_DEFS", "").split()      # experiment knobs, e.g. CGP_BUILD_DEFS="-DCGP64_GRID_U=1"
+    units = [(src, list(extra), src.replace(".cu", ".o")) for src in SOURCES]
     # the static N <= 64 kernel: one translation unit per (dim, task), built in parallel
-    units += [("cgp_small64.cu", ["-DCGP64_DIM=%d" % d, "-DCGP64_TASK=%d" % t], "cgp_small64_d%d_t%d.o" % (d, t))
-              for d in (1, 2) for t in (0, 1, 2, 4, 5)] + [("cgp_small64.cu", ["-DCGP64_DIM=1", "-DCGP64_TASK=%d" % t], "cgp_small64_d1_t%d.o" % t) for t in (6, 7)]
+    units += [("cgp_small64.cu", extra + ["-DCGP64_DIM=%d" % d, "-DCGP64_TASK=%d" % t], "cgp_small64_d%d_t%d.o" % (d, t))
+              for d in (1, 2) for t in (0, 1, 2, 4, 5)] + [("cgp_small64.cu", extra + ["-DCGP64_DIM=1", "-DCGP64_TASK=%d" % t], "cgp_small64_d1_t%d.o" % t) for t in (6, 7)]
     for src, defs, objname in units:
         obj = os.path.join(CSRC, objname)
         cmd = ([_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else [])

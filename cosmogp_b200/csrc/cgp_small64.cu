@@ -35,6 +35,10 @@
 #include <stdlib.h>
 #include <type_traits>
 
+#ifndef CGP64_GRID_U
+#define CGP64_GRID_U 2            // blocks of 8 grid points per pass of the prediction kernels
+#endif
+
 namespace cgp {
 namespace {
 
@@ -595,16 +599,17 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     }
 
     if (FUSED || PF) {
-      // ---------------- two blocks of 8 grid points per pass
+      // ---------------- U blocks of 8 grid points per pass (CGP64_GRID_U, 1 or 2)
+      constexpr int U = CGP64_GRID_U;
       const int64_t g0 = a.goff ? a.goff[b] : 0;
       const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
       const int64_t out0 = a.goff ? g0 : b * a.m_shared;
       const int64_t n_rb = (m_pts + 7) >> 3;
       const double amp_star = cov.amp_auto + cov.nugget2;
-      double pgx[2], pgy[2], pny0[2];
+      double pgx[U], pgy[U], pny0[U];
       auto grid_fetch = [&](int64_t rb) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int64_t m = 8 * (rb + u) + L.g;
           const bool lv = m < m_pts;
           pgx[u] = 0.0; pgy[u] = 0.0;
@@ -615,12 +620,12 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           pny0[u] = (lv && a.new_y0) ? (a.new_y0_diff ? a.new_y0[m] + a.new_y0_diff[b] : a.new_y0[out0 + m]) : 0.0;
         }
       };
-      const int64_t rb0 = (int64_t)(part * WPC + warp) * 2, rbs = (int64_t)split * WPC * 2;   // the warps of a CTA alternate over the passes
+      const int64_t rb0 = (int64_t)(part * WPC + warp) * U, rbs = (int64_t)split * WPC * U;   // the warps of a CTA alternate over the passes
       grid_fetch(rb0);
       for (int64_t rb = rb0; rb < n_rb; rb += rbs) {
-        int64_t mi[2]; bool live[2]; double gx[2], gy[2], ny0[2];
+        int64_t mi[U]; bool live[U]; double gx[U], gy[U], ny0[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
           mi[u] = 8 * (rb + u) + L.g;
           live[u] = mi[u] < m_pts;
           gx[u] = pgx[u]; gy[u] = pgy[u]; ny0[u] = pny0[u];
@@ -628,9 +633,13 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         grid_fetch(rb + rbs);                              // next pair's coordinates, behind this pair's math
         // cross-covariance fragments (no amplitude), generated straight into the accumulators of the forward
         // substitution: lane (g,t) holds H[grid row g][columns 8P+2t, 8P+2t+1] = the start value of W_P
-        double acc0[2][NB], acc1[2][NB];
+        double acc0[U][NB], acc1[U][NB];
         if constexpr (UNI) {
           double2* anch = reinterpret_cast<double2*>(px);      // {E_a, R} per object point (px + noise: 2 LD doubles)
+          // the anchors serve 16 grid rows: with one block per pass they are computed for every even block and the odd
+          // block that follows reuses them (rows g + 8); blocks that do not follow each other (split > 1) get their own
+          const bool second = (U == 1) && (rbs == 1) && (rb & 1);
+          if (!second) {
           __syncwarp();                                        // the previous pass has read its anchors
           const double gj0 = fma((double)(8 * rb), uni_delta, uni_g0);
 #pragma unroll
@@ -645,6 +654,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
             if (c < LD) anch[c] = make_double2(ea, rr);
           }
           __syncwarp();
+          }
           const bool b1 = L.g & 1, b2 = L.g & 2, b4 = L.g & 4;
 #pragma unroll
           for (int P = 0; P < NB; ++P) {
@@ -657,9 +667,14 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
             if (b2) { p0 *= r02; p1 *= r12; }
             if (b4) { p0 *= r04; p1 *= r14; }
             const double t0 = A0.x * p0, t1 = A1.x * p1;
-            const double e00 = t0 * uni_c0, e01 = (t0 * r08) * uni_c1;
-            const double e10 = t1 * uni_c0, e11 = (t1 * r18) * uni_c1;
-            acc0[0][P] = e00; acc0[1][P] = e01; acc1[0][P] = e10; acc1[1][P] = e11;
+            if constexpr (U == 2) {
+              const double e00 = t0 * uni_c0, e01 = (t0 * r08) * uni_c1;
+              const double e10 = t1 * uni_c0, e11 = (t1 * r18) * uni_c1;
+              acc0[0][P] = e00; acc0[1][P] = e01; acc1[0][P] = e10; acc1[1][P] = e11;
+            } else {
+              const double cs = second ? uni_c1 : uni_c0;
+              acc0[0][P] = (second ? t0 * r08 : t0) * cs; acc1[0][P] = (second ? t1 * r18 : t1) * cs;
+            }
           }
         } else {
 #pragma unroll
@@ -670,7 +685,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           double y0c = 0.0, y1c = 0.0;
           if (DIM == 2) { const double2 yy = ld_vec2(px + LD, c0); y0c = yy.x; y1c = yy.y; }
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < U; ++u) {
             double e0 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x0, y0c));
             double e1 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x1, y1c));
             e0 = (live[u] && c0 < n) ? e0 : 0.0;
@@ -681,13 +696,15 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         }
         // block forward substitution L v = h on the tensor cores (see the NEGL note): block P is finished by
         // V_P = W_P T_P^T, then added into every later block through the stored -L[J][P]; mean = v . z, var = amp* - |v|^2
-        double pm[2] = {0.0, 0.0}, pm2[2] = {0.0, 0.0}, vs[2] = {0.0, 0.0}, vs2[2] = {0.0, 0.0};
+        double pm[U], pm2[U], vs[U], vs2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { pm[u] = 0.0; pm2[u] = 0.0; vs[u] = 0.0; vs2[u] = 0.0; }
 #pragma unroll
         for (int P = 0; P < NB; ++P) {
           const double2 ft = ld_frag(tiles, slot(P, P), L);
           const double2 zz = ld_vec2(va, 8 * P + 2 * L.t);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < U; ++u) {
             double v0 = 0.0, v1 = 0.0;
             dmma(v0, v1, acc0[u][P], ft.x); dmma(v0, v1, acc1[u][P], ft.y);
             acc0[u][P] = v0; acc1[u][P] = v1;
@@ -699,12 +716,14 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
 #pragma unroll
           for (int J = P + 1; J < NB; ++J) {
             const double2 fb = ld_frag(tiles, slot(J, P), L);
-            dmma(acc0[0][J], acc1[0][J], acc0[0][P], fb.x); dmma(acc0[1][J], acc1[1][J], acc0[1][P], fb.x);
-            dmma(acc0[0][J], acc1[0][J], acc1[0][P], fb.y); dmma(acc0[1][J], acc1[1][J], acc1[1][P], fb.y);
+#pragma unroll
+            for (int u = 0; u < U; ++u) dmma(acc0[u][J], acc1[u][J], acc0[u][P], fb.x);
+#pragma unroll
+            for (int u = 0; u < U; ++u) dmma(acc0[u][J], acc1[u][J], acc1[u][P], fb.y);
           }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
           double vv = vs[u], vv2 = vs2[u];
           const double pmt = red_t(pm[u] + pm2[u]);
           vv = red_t(vv + vv2);
