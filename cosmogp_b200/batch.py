@@ -326,7 +326,7 @@ class DeviceBatch:
 
     def factor_dev(self, hyp, nugget=0.0, floor=0.0, flags=0, want_ll=False):
         """Factorise every object once (objects of <= 64 points): returns an opaque device workspace
-        holding inv(L) and alpha, reusable by predict_factored_dev for any number of grids.
+        holding the Cholesky factor and z = L^-1 (y - y0), reusable by predict_factored_dev for any number of grids.
         want_ll: also return each object's log-likelihood (fac["ll"], device) from the same factorisation."""
         assert 0 < self.max_n <= 64, "factor_dev handles objects of 1..64 points"
         h = self._hyp(hyp)

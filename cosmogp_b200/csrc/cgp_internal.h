@@ -41,7 +41,8 @@ __host__ __device__ inline Cov cov_from_hyp(int dim, const double* hyp, double n
   return c;
 }
 
-// TASK_FACTOR writes L^-1 (fragment-order tiles) + alpha per object to a workspace; TASK_PREDICT_F
+// TASK_FACTOR writes the Cholesky factor (T_J = L_JJ^-1 on the diagonal, -L[I][J] below, in the tile layout of
+// cgp_small64.cu) + z = L^-1 r per object to a workspace; TASK_PREDICT_F
 // predicts from that workspace (staged into shared memory by one TMA bulk copy per object).
 // TASK_PREDICT_FU: TASK_PREDICT_F for dim 1 on a uniformly spaced shared grid with l >= spacing (exps by recurrence).
 // TASK_PREDICT_U: TASK_PREDICT (factorise + predict in ONE pass, nothing spilled) on a uniform shared 1D grid; like

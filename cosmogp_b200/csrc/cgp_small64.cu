@@ -205,8 +205,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
 
   const int split = (FUSED || PF) ? a.split : 1;
   const int64_t n_work = (a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj) * split;
-  // factor workspace of one object: NT tiles in fragment order followed by alpha (LD doubles)
-  constexpr int WS = NT * TILE + LD;
+  // factor workspace of one object: NT tiles (T_J on the diagonal, -L[I][J] below) followed by z (LD doubles)
   __shared__ __align__(8) unsigned long long s_mbar;       // TMA completion barrier (TASK_PREDICT_F)
   __shared__ long long s_tk[2];                            // WPC > 1: the ticket drawn by thread 0, double buffered
   unsigned mbar_parity = 0;
@@ -304,7 +303,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
     double lp_m = 1.0; int lp_e = 0; int bad = 0;
     const bool want_u = (TASK == TASK_LOO) && (a.loo_mode == 1);
     if (PF) {
-      // L^-1 tiles + alpha of this object: one TMA bulk copy global -> shared, completion on an mbarrier
+      // factor tiles + z of this object: one TMA bulk copy each, global -> shared, completion on an mbarrier
       const unsigned mb = (unsigned)__cvta_generic_to_shared(&s_mbar);
       if (threadIdx.x == 0) {
         const unsigned bytes = NT * TILE * 8;

@@ -194,8 +194,9 @@ int cgp_step_batched_dev(int64_t n_obj, const int64_t* off, int max_n, int dim,
                          const double* new_y0, double* ll_obj, double* mean, double* var, int* info, void* stream);
 
 /* ---- factor once, predict on any number of grids (objects of <= 64 points): the two halves of
- *      cgp_predict_batched_dev as separate calls.  ws holds, per object, inv(L) as 8x8 tiles in DMMA
- *      fragment order followed by alpha = K^-1 (y - y0): cgp_factor_ws_doubles(max_n) doubles each.
+ *      cgp_predict_batched_dev as separate calls.  ws holds, per object, the Cholesky factor as 8x8 tiles in the
+ *      kernels' tile layout (inv(L_JJ) on the diagonal, -L[I][J] below) followed by z = L^-1 (y - y0): an opaque
+ *      block of cgp_factor_ws_doubles(max_n) doubles each, to be consumed by cgp_predict_factored_dev only.
  *      cgp_predict_factored_dev stages each object's factor into shared memory with one TMA bulk
  *      copy; var may be NULL.  hyp / nugget / flags must be those used for the factorisation.
  *      ll_obj (may be NULL) receives each object's log-likelihood (Gaussian_process.py:13-75) from the
