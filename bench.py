@@ -451,10 +451,11 @@ def main():
 
     # ---- end to end through the numpy-in/numpy-out layer: every step uploads the step's inputs from
     # pinned host memory, runs LL + predict and downloads ll/mean/var; chunks of objects (ramping up from
-    # 2048 to a quarter of the batch and down again) are pipelined: one upload stream, one download stream,
-    # kernels of consecutive chunks on 8 compute streams -- one native call per step (cgp_streamer_run)
+    # 2048 to a sixteenth of the batch and down again) are pipelined: one upload stream, one download stream,
+    # kernels of consecutive chunks on 8 compute streams -- one native call per step (cgp_streamer_run); a chunk of
+    # x | y | y_err travels as ONE two-dimensional copy, mean | var likewise, the per-object scalars once per run
     from cosmogp_b200.batch import StreamedEvaluator
-    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "8")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "8")), shared_mean=True)
+    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "16")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "8")), shared_mean=True)
     for name, arr in (("x", x), ("y", y), ("y_err", ye), ("template", tmpl), ("diff", d)):
         ev_e2e.host(name)[...] = arr
     # the mean at the epochs (template spline + offset, cosmogp/mean.py:84-90) is evaluated on the device from the

@@ -501,8 +501,13 @@ class StreamedEvaluator:
         xs = (self.B, self.N, 2) if dim == 2 else (self.B, self.N)
         pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
         self.shared_mean = bool(shared_mean)
-        self.h = {"x": pin(*xs), "y": pin(self.B, self.N), "y0": pin(self.B, self.N), "y_err": pin(self.B, self.N),
-                  "ll": pin(self.B), "mean": pin(self.B, self.M), "var": pin(self.B, self.M)}
+        # x | y | y_err | y0 as rows of ONE pinned block, mean | var of another: a chunk of all of them then travels as one
+        # two-dimensional copy (with both directions of the link busy every extra copy costs ~20 us: cgp_stream.cu)
+        self._in = pin(3 if dim == 2 else 4, self.B, self.N)
+        self._out = pin(2, self.B, self.M)
+        rows = (None, 0, 1, 2) if dim == 2 else (0, 1, 2, 3)
+        self.h = {"x": pin(*xs) if dim == 2 else self._in[0], "y": self._in[rows[1]], "y_err": self._in[rows[2]],
+                  "y0": self._in[rows[3]], "ll": pin(self.B), "mean": self._out[0], "var": self._out[1]}
         if self.shared_mean:
             self._packed_mean = pin(self.M + self.B)                # [template | offsets], what CGP_MEAN_TEMPLATE reads
             self.h["template"], self.h["diff"] = self._packed_mean[:self.M], self._packed_mean[self.M:]

@@ -467,7 +467,8 @@ int cgp_predict_factored_dev(int64_t n_obj, const int64_t* off, int max_n, int d
 int cgp::predict_factored(int64_t n_obj, const int64_t* off, int max_n, int dim, const double* x,
                           const double* hyp, double nugget, unsigned flags, const double* ws, const int* info,
                           const double* xnew, const int64_t* goff, int64_t m_shared,
-                          const double* new_y0, double* mean, double* var, int uniform, void* stream) {
+                          const double* new_y0, double* mean, double* var, int uniform, void* stream,
+                          const double* template_offsets) {
   if (n_obj < 0 || (n_obj && (!off || !x || !ws || !info || !xnew || !mean)))
     return fail(CGP_ERR_ARG, "cgp_predict_factored_dev: NULL argument");
   if (max_n <= 0 || max_n > 64) return fail(CGP_ERR_SIZE, "cgp_predict_factored_dev: objects of 1..64 points only (max_n = %d)", max_n);
@@ -479,7 +480,7 @@ int cgp::predict_factored(int64_t n_obj, const int64_t* off, int max_n, int dim,
   a.xnew = xnew; a.goff = goff; a.m_shared = m_shared; a.new_y0 = new_y0; a.mean = mean; a.var = var;
   if ((flags & CGP_MEAN_TEMPLATE) && new_y0) {
     if (goff) return fail(CGP_ERR_ARG, "CGP_MEAN_TEMPLATE needs a shared grid (goff == NULL)");
-    a.new_y0_diff = new_y0 + m_shared;
+    a.new_y0_diff = template_offsets ? template_offsets : new_y0 + m_shared;
   }
   int split = 1;
   if (!goff && n_obj < 296) {

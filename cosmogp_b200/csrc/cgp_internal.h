@@ -163,7 +163,8 @@ int uniform_grid_ok(const double* grid_host, int64_t m, const double* hyp);
 int predict_factored(int64_t n_obj, const int64_t* off, int max_n, int dim, const double* x,
                      const double* hyp, double nugget, unsigned flags, const double* ws, const int* info,
                      const double* xnew, const int64_t* goff, int64_t m_shared,
-                     const double* new_y0, double* mean, double* var, int uniform, void* stream);
+                     const double* new_y0, double* mean, double* var, int uniform, void* stream,
+                     const double* template_offsets = nullptr);   // CGP_MEAN_TEMPLATE: offsets from here instead of new_y0 + m_shared
 
 // records the message cgp_last_error() returns (thread-local) and hands back `code` (cgp_api.cu)
 int fail(int code, const char* fmt, ...);

@@ -36,6 +36,13 @@ struct cgp_streamer {
   // several streams share the link, so the first (small) chunk would arrive no sooner than the ones behind it
   cudaStream_t up = nullptr, dn = nullptr;
   double* spl_t = nullptr; double* spl_c = nullptr; int spl_n = 0;     // mean template as a cubic B-spline (optional)
+  // Few and large copies: with both directions of the link busy every additional copy costs ~20 us of transfer time
+  // (tools/microbench_wc.cu: 144 MB each way take 3.0 ms as one copy, 3.7 ms as 13, 4.2 ms as 52).  So the per-object
+  // scalars live in arrays for the WHOLE batch (the log-likelihoods and info flags leave in one copy each at the end of
+  // a run, the mean template and its per-object offsets arrive in one copy at the start), and the per-point inputs /
+  // per-grid-point outputs of a chunk travel as ONE two-dimensional copy each when the caller's arrays are rows of one
+  // pinned block (x, y, y_err [, y0] and mean, var at a constant pitch: what StreamedEvaluator allocates).
+  double* ll_all = nullptr; int* info_all = nullptr; double* tmpl_all = nullptr; int64_t cap_all = 0;
 };
 
 namespace {
@@ -91,8 +98,7 @@ void release(cgp_streamer* s) {
   DeviceGuard g(s->dev);
   for (auto& k : s->slots) {
     if (k.st) cudaStreamSynchronize(k.st);
-    for (double* p : {k.x, k.y, k.y0, k.ye, k.ny0, k.ll, k.mean, k.var, k.ws}) if (p) cudaFree(p);
-    if (k.info) cudaFree(k.info);
+    for (double* p : {k.x, k.ny0, k.mean, k.ws}) if (p) cudaFree(p);
     if (k.st) cudaStreamDestroy(k.st);
     for (cudaEvent_t ev : {k.up_done, k.kern_done, k.dn_done}) if (ev) cudaEventDestroy(ev);
   }
@@ -102,6 +108,9 @@ void release(cgp_streamer* s) {
   if (s->grid) cudaFree(s->grid);
   if (s->spl_t) cudaFree(s->spl_t);
   if (s->spl_c) cudaFree(s->spl_c);
+  if (s->ll_all) cudaFree(s->ll_all);
+  if (s->info_all) cudaFree(s->info_all);
+  if (s->tmpl_all) cudaFree(s->tmpl_all);
   delete s;
 }
 
@@ -138,15 +147,11 @@ int cgp_streamer_create(int64_t chunk_objects, int n_pts, int64_t m_grid, int di
     e = cudaStreamCreateWithFlags(&k.st, cudaStreamNonBlocking);
     for (cudaEvent_t* ev : {&k.up_done, &k.kern_done, &k.dn_done})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = dalloc(&k.x, c * n * dim);
-    if (e == cudaSuccess) e = dalloc(&k.y, c * n);
-    if (e == cudaSuccess) e = dalloc(&k.y0, c * n);
-    if (e == cudaSuccess) e = dalloc(&k.ye, c * n);
-    if (e == cudaSuccess) e = dalloc(&k.ny0, c * m + m);        // rows per object, or [template | offsets]
-    if (e == cudaSuccess) e = dalloc(&k.ll, c);
-    if (e == cudaSuccess) e = dalloc(&k.mean, c * m);
-    if (e == cudaSuccess) e = dalloc(&k.var, c * m);
-    if (e == cudaSuccess) e = dalloc(&k.info, c);
+    if (e == cudaSuccess) e = dalloc(&k.x, c * n * (dim + 3));   // rows x | y | y_err | y0 at a pitch of c*n doubles (dim 1)
+    if (e == cudaSuccess) { k.y = k.x + c * n * dim; k.ye = k.y + c * n; k.y0 = k.ye + c * n; }
+    if (e == cudaSuccess) e = dalloc(&k.ny0, c * m + m);        // rows per object (mean function given as (B, M))
+    if (e == cudaSuccess) e = dalloc(&k.mean, 2 * c * m);       // rows mean | var at a pitch of c*m doubles
+    if (e == cudaSuccess) k.var = k.mean + c * m;
     if (e == cudaSuccess && s->two_kernel) e = dalloc(&k.ws, c * (size_t)cgp_factor_ws_doubles(n_pts));
   }
   if (e == cudaSuccess) {
@@ -202,10 +207,29 @@ int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
   auto d2h = [&](void* h, const void* d, size_t bytes, cudaStream_t st) {
     if (e == cudaSuccess && bytes) { e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st); down += (int64_t)bytes; }
   };
+  // whole-batch arrays for the per-object scalars (see cgp_streamer): grown on demand
+  if (n_obj > s->cap_all) {
+    for (void* p : {(void*)s->ll_all, (void*)s->info_all, (void*)s->tmpl_all}) if (p) cudaFree(p);
+    s->ll_all = nullptr; s->info_all = nullptr; s->tmpl_all = nullptr; s->cap_all = 0;
+    e = dalloc(&s->ll_all, (size_t)n_obj);
+    if (e == cudaSuccess) e = dalloc(&s->info_all, (size_t)n_obj);
+    if (e == cudaSuccess) e = dalloc(&s->tmpl_all, (size_t)n_obj + m);
+    if (e != cudaSuccess) return sfail(-100 - (int)e, "cgp_streamer_run (per-object arrays)", e);
+    s->cap_all = n_obj;
+  }
   if (m && n_obj) {
     h2d(s->grid, xnew, m * dim * 8, s->up);          // ahead of every chunk on the upload stream
+    if (tmpl) h2d(s->tmpl_all, new_y0, (m + (size_t)n_obj) * 8, s->up);      // template + every object's offset: one copy per run
   }
-  for (auto& k : s->slots) k.has_template = false;
+  // the caller's per-point arrays as rows of one pinned block (x | y | y_err [| y0] at a constant pitch, dim 1)?  Then a
+  // chunk of all of them is ONE two-dimensional copy; the same for the outputs (mean | var)
+  const ptrdiff_t pitch_in = y - x;
+  const bool in2d = dim == 1 && y_err && pitch_in >= (ptrdiff_t)(n_obj * (int64_t)n) && y_err - y == pitch_in &&
+                    (!y0 || y0 - y_err == pitch_in);
+  const int rows_in = y0 ? 4 : 3;
+  const ptrdiff_t pitch_out = (m && var) ? var - mean : 0;
+  const bool out2d = m && var && pitch_out >= (ptrdiff_t)(n_obj * (int64_t)m);
+  const size_t cap = (size_t)s->chunk;
   const std::vector<int64_t> sizes = chunk_schedule(n_obj, s->chunk, s->two_kernel);
   // CGP_STREAM_TRACE=1: per-chunk timeline (upload / kernels / download, ms since the start of the run) on stderr
   static const bool trace = getenv("CGP_STREAM_TRACE") != nullptr;
@@ -217,6 +241,7 @@ int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
   }
   auto mark = [&](int64_t chunk, int which, cudaStream_t st) { if (trace) cudaEventRecord(ev[(size_t)(4 * chunk + which)], st); };
   int64_t chunk_index = 0, a = 0;
+  cudaEvent_t last_kern = nullptr;
   for (; chunk_index < (int64_t)sizes.size() && e == cudaSuccess && rc >= 0; a += sizes[(size_t)chunk_index], ++chunk_index) {
     const size_t nb = (size_t)sizes[(size_t)chunk_index];
     cgp_streamer::Slot& k = s->slots[(size_t)(chunk_index % s->n_streams)];
@@ -224,62 +249,83 @@ int cgp_streamer_run(cgp_streamer* s, int64_t n_obj,
     const bool reused = chunk_index >= s->n_streams;  // the slot's previous chunk must be done with the buffers
     if (reused) e = cudaStreamWaitEvent(s->up, k.kern_done, 0);
     mark(chunk_index, 0, s->up);
-    h2d(k.x, x + (size_t)a * n * dim, nb * n * dim * 8, s->up);
-    h2d(k.y, y + (size_t)a * n, nb * n * 8, s->up);
-    if (y0) h2d(k.y0, y0 + (size_t)a * n, nb * n * 8, s->up);
-    if (y_err) h2d(k.ye, y_err + (size_t)a * n, nb * n * 8, s->up);
-    if (m && new_y0) {
-      if (tmpl) {
-        if (!k.has_template) { h2d(k.ny0, new_y0, m * 8, s->up); k.has_template = true; }
-        h2d(k.ny0 + m, new_y0 + m + (size_t)a, nb * 8, s->up);
-      } else {
-        h2d(k.ny0, new_y0 + (size_t)a * m, nb * m * 8, s->up);
+    if (in2d) {
+      if (e == cudaSuccess) {
+        e = cudaMemcpy2DAsync(k.x, cap * n * 8, x + (size_t)a * n, (size_t)pitch_in * 8, nb * n * 8, (size_t)rows_in,
+                              cudaMemcpyHostToDevice, s->up);
+        up += (int64_t)(rows_in * nb * n * 8);
       }
+    } else {
+      h2d(k.x, x + (size_t)a * n * dim, nb * n * dim * 8, s->up);
+      h2d(k.y, y + (size_t)a * n, nb * n * 8, s->up);
+      if (y0) h2d(k.y0, y0 + (size_t)a * n, nb * n * 8, s->up);
+      if (y_err) h2d(k.ye, y_err + (size_t)a * n, nb * n * 8, s->up);
     }
+    if (m && new_y0 && !tmpl) h2d(k.ny0, new_y0 + (size_t)a * m, nb * m * 8, s->up);
     if (e != cudaSuccess) break;
     mark(chunk_index, 1, s->up);
     if ((e = cudaEventRecord(k.up_done, s->up)) != cudaSuccess) break;
     if ((e = cudaStreamWaitEvent(cs, k.up_done, 0)) != cudaSuccess) break;
     if (reused && (e = cudaStreamWaitEvent(cs, k.dn_done, 0)) != cudaSuccess) break;   // outputs still downloading
     const double* dy0 = y0 ? k.y0 : nullptr;
+    const double* doffs = tmpl ? s->tmpl_all + m + a : nullptr;     // this chunk's offsets of the template mean
     if (!y0 && s->spl_n && tmpl) {                   // mean at the epochs = spline(x) + the object's offset, on the device
-      rc = cgp_spline_mean_dev(s->spl_t, s->spl_c, s->spl_n, k.x, (int64_t)(nb * n), s->off, (int64_t)nb, k.ny0 + m, k.y0, cs);
+      rc = cgp_spline_mean_dev(s->spl_t, s->spl_c, s->spl_n, k.x, (int64_t)(nb * n), s->off, (int64_t)nb, doffs, k.y0, cs);
       if (rc < 0) break;
       dy0 = k.y0;
     }
     const double* dye = y_err ? k.ye : nullptr;
-    const double* dny0 = (m && new_y0) ? k.ny0 : nullptr;
     double* dvar = var ? k.var : nullptr;
+    double* dll = s->ll_all + a; int* dinfo = s->info_all + a;
     const bool fused_ll = m && s->two_kernel;        // the factor kernel emits the likelihood too: one factorisation
     if (!fused_ll) {
       rc = cgp_ll_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, kflags,
-                              k.ll, k.info, cs);
+                              dll, dinfo, cs);
       if (rc < 0) break;
     }
     if (m) {
       if (s->two_kernel) {
         rc = cgp_factor_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, kflags,
-                                    k.ws, k.ll, k.info, cs);
+                                    k.ws, dll, dinfo, cs);
         if (rc < 0) break;
-        rc = cgp::predict_factored((int64_t)nb, s->off, s->n_pts, s->dim, k.x, hyp, nugget, pflags, k.ws, k.info,
-                                   s->grid, nullptr, (int64_t)m, dny0, k.mean, dvar, uniform, cs);
+        rc = cgp::predict_factored((int64_t)nb, s->off, s->n_pts, s->dim, k.x, hyp, nugget, pflags, k.ws, dinfo,
+                                   s->grid, nullptr, (int64_t)m, tmpl ? s->tmpl_all : (new_y0 ? k.ny0 : nullptr), k.mean, dvar,
+                                   uniform, cs, doffs);
       } else {
+        const double* dny0 = nullptr;
+        if (new_y0 && tmpl) {                        // the public entry point takes [template | offsets] in one array
+          cudaMemcpyAsync(k.ny0, s->tmpl_all, m * 8, cudaMemcpyDeviceToDevice, cs);
+          cudaMemcpyAsync(k.ny0 + m, doffs, nb * 8, cudaMemcpyDeviceToDevice, cs);
+          dny0 = k.ny0;
+        } else if (new_y0) dny0 = k.ny0;
         rc = cgp_predict_batched_dev((int64_t)nb, s->off, s->n_pts, s->dim, k.x, k.y, dy0, dye, hyp, nugget, floor, pflags,
-                                     s->grid, nullptr, (int64_t)m, dny0, k.mean, dvar, k.info, cs);
+                                     s->grid, nullptr, (int64_t)m, dny0, k.mean, dvar, dinfo, cs);
       }
       if (rc < 0) break;
     }
     mark(chunk_index, 2, cs);
     if ((e = cudaEventRecord(k.kern_done, cs)) != cudaSuccess) break;
+    last_kern = k.kern_done;
     if ((e = cudaStreamWaitEvent(s->dn, k.kern_done, 0)) != cudaSuccess) break;
-    d2h(ll + a, k.ll, nb * 8, s->dn);
     if (m) {
-      d2h(mean + (size_t)a * m, k.mean, nb * m * 8, s->dn);
-      if (var) d2h(var + (size_t)a * m, k.var, nb * m * 8, s->dn);
+      if (out2d) {
+        e = cudaMemcpy2DAsync(mean + (size_t)a * m, (size_t)pitch_out * 8, k.mean, cap * m * 8, nb * m * 8, 2,
+                              cudaMemcpyDeviceToHost, s->dn);
+        down += (int64_t)(2 * nb * m * 8);
+      } else {
+        d2h(mean + (size_t)a * m, k.mean, nb * m * 8, s->dn);
+        if (var) d2h(var + (size_t)a * m, k.var, nb * m * 8, s->dn);
+      }
     }
-    d2h(info + a, k.info, nb * 4, s->dn);
     mark(chunk_index, 3, s->dn);
     if (e == cudaSuccess) e = cudaEventRecord(k.dn_done, s->dn);
+  }
+  // the per-object scalars of the whole batch: one copy each, behind the last chunk's kernels (the download stream has
+  // waited for every chunk's kernels in order)
+  if (e == cudaSuccess && rc >= 0 && n_obj) {
+    if (!m && last_kern) e = cudaStreamWaitEvent(s->dn, last_kern, 0);
+    d2h(ll, s->ll_all, (size_t)n_obj * 8, s->dn);
+    d2h(info, s->info_all, (size_t)n_obj * 4, s->dn);
   }
   for (cudaStream_t st : {s->up, s->dn}) {        // always drain, also after an error
     cudaError_t se = cudaStreamSynchronize(st);

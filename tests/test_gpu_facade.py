@@ -369,7 +369,7 @@ def test_streamed_evaluator_matches_resident_batch(cg):
     m4, v4, _ = batch.predict([0.5, 2.0], 0.03, grid, new_y0=tmpl[None, :] + diff[:, None])
     assert tot3 == t2
     assert_close(mean3, m4, 1e-10, 1e-11); assert_close(var3, v4, 1e-10, 1e-11)
-    assert ev2.h2d_bytes == (b * (4 * n + 1) + 3 * m + m) * 8                # template once per stream, grid once
+    assert ev2.h2d_bytes == (b * (4 * n + 1) + m + m) * 8                    # template and offsets once per run, grid once
     # large chunks: ramped schedule (2048, 3276, ... up to the buffer capacity, then down again), two-kernel route
     b, n, m = 40001, 20, 16
     x = np.sort(rng.uniform(-10, 40, (b, n)), axis=1); y = rng.standard_normal((b, n)); ye = np.full((b, n), 0.2)
