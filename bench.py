@@ -455,7 +455,8 @@ def main():
     # kernels of consecutive chunks on 8 compute streams -- one native call per step (cgp_streamer_run); a chunk of
     # x | y | y_err travels as ONE two-dimensional copy, mean | var likewise, the per-object scalars once per run
     from cosmogp_b200.batch import StreamedEvaluator
-    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=int(os.environ.get("CGP_E2E_CHUNKS", "16")), n_streams=int(os.environ.get("CGP_E2E_STREAMS", "8")), shared_mean=True)
+    n_chunks = int(os.environ.get("CGP_E2E_CHUNKS", "0")) or max(1, min(16, B // 4096))     # chunks stay on the two-kernel route (>= 2048 objects)
+    ev_e2e = StreamedEvaluator(B, N_EPOCH, M_GRID, dim=1, n_chunks=n_chunks, n_streams=int(os.environ.get("CGP_E2E_STREAMS", "8")), shared_mean=True)
     for name, arr in (("x", x), ("y", y), ("y_err", ye), ("template", tmpl), ("diff", d)):
         ev_e2e.host(name)[...] = arr
     # the mean at the epochs (template spline + offset, cosmogp/mean.py:84-90) is evaluated on the device from the
