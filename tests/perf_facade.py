@@ -1,5 +1,5 @@
 """Wall clock of the numpy-in / numpy-out facade at C2 (10^5 x 60, shared mean) and at C1 (one object of 50 points):
-construction, one likelihood evaluation, a full find_hyperparameters, get_prediction.  python tools/bench_facade_c2.py"""
+construction, one likelihood evaluation, a full find_hyperparameters, get_prediction.  python tests/perf_facade.py"""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,5 +1,5 @@
 """Resident C2 step, kernel variants side by side (CUDA events): separate LL kernel, factor(+LL) + grid kernel,
-and the single fused kernel (cgp_step_batched_dev).  python tools/bench_step.py [objects] [reps]"""
+and the single fused kernel (cgp_step_batched_dev).  python tests/perf_step.py [objects] [reps]"""
 import json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
