@@ -660,7 +660,12 @@ int launch_cfg(int nbm, const SmallArgs& a, cudaStream_t stream) {
     return launch_one<DIM, TASK, 8, 1>(nbm, a, stream);
   }
   if (nbm <= 16) return launch_one<DIM, TASK, 16, 4>(nbm, a, stream);
-  return launch_one<DIM, TASK, 28, 4>(nbm, a, stream);
+  // above 128 points one object fills the shared memory of an SM: eight warps (two per sub-partition) instead of four
+  // hide more of each other's dependent chains (CGP_BIG_WARPS=4 for the round-1 shape)
+  static int big = -1;
+  if (big < 0) { const char* e = getenv("CGP_BIG_WARPS"); big = (e && atoi(e) == 4) ? 4 : 8; }
+  if (big == 4 || TASK == TASK_MATRICES) return launch_one<DIM, TASK, 28, 4>(nbm, a, stream);
+  return launch_one<DIM, TASK, 28, 8>(nbm, a, stream);
 }
 
 template <int DIM>
