@@ -659,7 +659,12 @@ int launch_cfg(int nbm, const SmallArgs& a, cudaStream_t stream) {
     if (w == 4) return launch_one<DIM, TASK, 8, 4>(nbm, a, stream);
     return launch_one<DIM, TASK, 8, 1>(nbm, a, stream);
   }
-  if (nbm <= 16) return launch_one<DIM, TASK, 16, 4>(nbm, a, stream);
+  static int mid = -1;
+  if (mid < 0) { const char* e = getenv("CGP_MID_WARPS"); mid = (e && atoi(e) == 8) ? 8 : 4; }
+  if (nbm <= 16) {
+    if (mid == 8 && TASK != TASK_MATRICES) return launch_one<DIM, TASK, 16, 8>(nbm, a, stream);
+    return launch_one<DIM, TASK, 16, 4>(nbm, a, stream);
+  }
   // above 128 points one object fills the shared memory of an SM: eight warps (two per sub-partition) instead of four
   // hide more of each other's dependent chains (CGP_BIG_WARPS=4 for the round-1 shape)
   static int big = -1;
