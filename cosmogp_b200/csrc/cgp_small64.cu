@@ -203,6 +203,10 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   double* v1 = vd + LD;
   double* vu = v1 + LD;
 
+  // the general-grid prediction from a stored factor never stages the noise vector: at NB = 8 its 64 doubles hold the
+  // table of the table-driven exp (cgp_math.cuh) for the cross-covariance entries (one exp per grid point and data point)
+  constexpr bool TAB = PF && !UNI && NB == 8 && WPC == 1;
+  if (TAB) { exp_table_to_shared(noise, lane); __syncwarp(); }
   const int split = (FUSED || PF) ? a.split : 1;
   const int64_t n_work = (a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj) * split;
   // factor workspace of one object: NT tiles (T_J on the diagonal, -L[I][J] below) followed by z (LD doubles)
@@ -685,8 +689,8 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           if (DIM == 2) { const double2 yy = ld_vec2(px + LD, c0); y0c = yy.x; y1c = yy.y; }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            double e0 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x0, y0c));
-            double e1 = cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x1, y1c));
+            double e0 = TAB ? cgp_exp_tab(rbf_arg<DIM>(cov, gx[u], gy[u], x0, y0c), noise) : cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x0, y0c));
+            double e1 = TAB ? cgp_exp_tab(rbf_arg<DIM>(cov, gx[u], gy[u], x1, y1c), noise) : cgp_exp(rbf_arg<DIM>(cov, gx[u], gy[u], x1, y1c));
             e0 = (live[u] && c0 < n) ? e0 : 0.0;
             e1 = (live[u] && c1 < n) ? e1 : 0.0;
             acc0[u][P] = e0; acc1[u][P] = e1;
@@ -777,6 +781,9 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   double* px = tiles + NSLOT * TILE;
   double* noise = px + DIM * LD;
   double* vr = noise + LD;
+  double* etab = vr + LD;                                 // 2^(j/64) for the table-driven exp (cgp_math.cuh)
+  exp_table_to_shared(etab, lane);
+  __syncwarp();
   const int64_t n_work = a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj;
 
   constexpr int NR = (LD + 31) / 32;
@@ -834,8 +841,8 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         constexpr int i = decltype(ic)::value;
         const int gi = 8 * (J + i) + L.g, cj = 8 * J + 2 * L.t;
         const double xi = px[gi], yi = DIM == 2 ? px[LD + gi] : 0.0;
-        double e0 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj], DIM == 2 ? px[LD + cj] : 0.0));
-        double e1 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj + 1], DIM == 2 ? px[LD + cj + 1] : 0.0));
+        double e0 = cgp_exp_tab(rbf_arg<DIM>(cov, xi, yi, px[cj], DIM == 2 ? px[LD + cj] : 0.0), etab);
+        double e1 = cgp_exp_tab(rbf_arg<DIM>(cov, xi, yi, px[cj + 1], DIM == 2 ? px[LD + cj + 1] : 0.0), etab);
         e0 = (gi < n && cj < gi) ? e0 : 0.0;
         e1 = (gi < n && cj + 1 < gi) ? e1 : 0.0;
         const double dg = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
@@ -918,7 +925,7 @@ gp64_ll_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
 template <int DIM, int NB>
 int launch64_ll(const SmallArgs& a, cudaStream_t stream) {
   auto kern = gp64_ll_kernel<DIM, NB>;
-  const size_t smem = ((size_t)kPhysSlots[NB - 1] * TILE + (size_t)(DIM + 2) * 8 * NB) * sizeof(double);
+  const size_t smem = ((size_t)kPhysSlots[NB - 1] * TILE + (size_t)(DIM + 2) * 8 * NB + 64) * sizeof(double);   // + the exp table
   static int sm_counts[16] = {0}, per_sms[16] = {0};   // per device of this process (function attributes are per device)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return (int)cudaErrorInvalidDevice;
