@@ -155,7 +155,13 @@ static unsigned long long* next_ticket(cudaStream_t stream) {
   return t;
 }
 
-constexpr int n_vec64(int task) { return task == TASK_LOO ? 6 : 1; }
+__host__ __device__ constexpr int n_vec64(int task) { return task == TASK_LOO ? 6 : 1; }
+// covariance phase of gp64_kernel with the table-driven exp (512 more bytes of shared memory per CTA) where that does not
+// cost an object per SM: the pulls kernel (9 objects per SM at NB = 8 either way, register-capped at 16 below) and the
+// one-pass kernels below NB = 8; at NB = 8 the 36-tile one-pass kernels have 139 bytes to spare before 11 objects become 10
+__host__ __device__ constexpr bool ktab64(int task, int nb) {
+  return task == TASK_LOO || ((task == TASK_PREDICT || task == TASK_PREDICT_U || task == TASK_LL) && nb < 8);
+}
 // Warps per CTA that share one staged factor in the grid kernels (see WPC in gp64_kernel).  Measured at C2 with 2: 16 warps
 // per SM on 8 factors, but 7 passes split 4 + 3 between the two warps, two CTA barriers per object and 128-register
 // spills: grid kernel 2.13 -> 2.42 ms.  Kept at 1 (CGP64_GRID_WPC=2 at compile time selects the shared form; tested).
@@ -207,6 +213,9 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   // table of the table-driven exp (cgp_math.cuh) for the cross-covariance entries (one exp per grid point and data point)
   constexpr bool TAB = PF && !UNI && NB == 8 && WPC == 1;
   if (TAB) { exp_table_to_shared(noise, lane); __syncwarp(); }
+  constexpr bool KTAB = ktab64(TASK, NB);
+  double* const ktab = tiles + NT * TILE + (WPC * (DIM + 1) + n_vec64(TASK)) * LD;      // behind the last vector
+  if (KTAB) { exp_table_to_shared(ktab, lane); __syncwarp(); }
   const int split = (FUSED || PF) ? a.split : 1;
   const int64_t n_work = (a.n_obj_dev ? (int64_t)*a.n_obj_dev : a.n_obj) * split;
   // factor workspace of one object: NT tiles (T_J on the diagonal, -L[I][J] below) followed by z (LD doubles)
@@ -343,8 +352,10 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
         const int gi = 8 * I + L.g, cj = 8 * J + 2 * L.t;
         const double xi = px[gi], yi = DIM == 2 ? px[LD + gi] : 0.0;
         // branch-free: a conditional exp would serialise the chains (ncu r01c: 34 % of the time)
-        double e0 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj], DIM == 2 ? px[LD + cj] : 0.0));
-        double e1 = cgp_exp(rbf_arg<DIM>(cov, xi, yi, px[cj + 1], DIM == 2 ? px[LD + cj + 1] : 0.0));
+        const double q0 = rbf_arg<DIM>(cov, xi, yi, px[cj], DIM == 2 ? px[LD + cj] : 0.0);
+        const double q1 = rbf_arg<DIM>(cov, xi, yi, px[cj + 1], DIM == 2 ? px[LD + cj + 1] : 0.0);
+        double e0 = KTAB ? cgp_exp_tab(q0, ktab) : cgp_exp(q0);
+        double e1 = KTAB ? cgp_exp_tab(q1, ktab) : cgp_exp(q1);
         e0 = (gi < n && cj < gi) ? e0 : 0.0;
         e1 = (gi < n && cj + 1 < gi) ? e1 : 0.0;
         const double dg = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
@@ -963,7 +974,8 @@ int launch64(const SmallArgs& a, cudaStream_t stream) {
   if ((TASK == TASK_LL && compact) || (TASK == TASK_FACTOR && fcompact)) return launch64_ll<DIM, NB>(a, stream);
   auto kern = gp64_kernel<DIM, TASK, NB>;
   constexpr int WPC = warps_per_cta(TASK);
-  const size_t smem = ((size_t)(NB * (NB + 1) / 2) * TILE + (size_t)(WPC * (DIM + 1) + n_vec64(TASK)) * 8 * NB) * sizeof(double);
+  const size_t smem = ((size_t)(NB * (NB + 1) / 2) * TILE + (size_t)(WPC * (DIM + 1) + n_vec64(TASK)) * 8 * NB
+                       + (ktab64(TASK, NB) ? 64 : 0)) * sizeof(double);
   static int sm_counts[16] = {0}, per_sms[16] = {0};   // per device of this process
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return (int)cudaErrorInvalidDevice;
