@@ -23,10 +23,8 @@ struct cgp_streamer {
   bool two_kernel = false;
   struct Slot {
     cudaStream_t st = nullptr;
-    double *x = nullptr, *y = nullptr, *y0 = nullptr, *ye = nullptr, *ny0 = nullptr, *ll = nullptr, *mean = nullptr,
-           *var = nullptr, *ws = nullptr;
-    int* info = nullptr;
-    bool has_template = false;
+    // x owns the input block (rows x | y | y_err | y0), mean the output block (rows mean | var); y, ye, y0, var point into them
+    double *x = nullptr, *y = nullptr, *y0 = nullptr, *ye = nullptr, *ny0 = nullptr, *mean = nullptr, *var = nullptr, *ws = nullptr;
     cudaEvent_t up_done = nullptr, kern_done = nullptr, dn_done = nullptr;
   };
   std::vector<Slot> slots;
