@@ -66,3 +66,27 @@ def test_shard_ranges_cover_and_balance():
         assert max(cost) < 1.1 * sum(cost) / parts + 200.0 ** 3
     assert multi.shard_ranges(np.array([0]), 3) == [(0, 0)] * 3
     assert multi.shard_ranges(np.array([0, 5]), 4)[0] == (0, 1)
+
+
+def test_reference_arm_times_the_unmodified_reference():
+    """`bench.py --impl reference` (the CPU arm the driver runs): a JSON line with impl == "reference" whose cpu_baseline
+    says kind == "reference" when baseline/_ref (or /root/reference) is present -- i.e. the numbers come from the
+    reference's own code, not from the oracle port."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from oracle import ref_loader
+    if not ref_loader.available():
+        import pytest
+        pytest.skip("no reference tree (baseline/_ref is installed by baseline/fetch_ref.py)")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-objects", "32"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "reference" and line["value"] > 0
+    assert line["metric"] == "gp_fits_per_sec" and line["unit"] == "objects/s" and line["gpu_launches"] == 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["svd_method_true"]["value"] > 0
+    # the installed copy under baseline/_ref is byte-identical to the reference tree when both are present
+    ref_root, inst = "/root/reference/cosmogp", os.path.join(root, "baseline", "_ref", "cosmogp")
+    if os.path.isdir(ref_root) and os.path.isdir(inst):
+        for name in ("Gaussian_process.py", "kernel.py", "inv_matrix.py", "mean.py", "pull.py", "__init__.py"):
+            assert open(os.path.join(ref_root, name), "rb").read() == open(os.path.join(inst, name), "rb").read(), name
