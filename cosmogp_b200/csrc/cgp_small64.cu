@@ -259,12 +259,14 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
   //   exp(h00 (g_j0 + k delta - x)^2) = E_a(x) * R(x)^k * C_k,  E_a = exp(h00 u^2), R = exp(2 h00 delta u), u = g_j0 - x,
   // C_k = exp(h00 k^2 delta^2): two exps per object point and pass instead of one per (grid row, object point).
   // The caller guarantees l >= |delta|: whenever E_a underflows every product it scales is < 1e-110.
-  double uni_g0 = 0.0, uni_delta = 0.0, uni_c0 = 1.0, uni_c1 = 1.0, uni_2hd = 0.0;
+  double uni_g0 = 0.0, uni_delta = 0.0, uni_c0 = 1.0, uni_c1 = 1.0, uni_c2 = 1.0, uni_2hd = 0.0;
   if (UNI) {
     uni_g0 = a.xnew[0];
     uni_delta = (a.xnew[a.m_shared - 1] - uni_g0) / (double)(a.m_shared - 1);
     const double k0 = (double)L.g * uni_delta, k1 = (double)(L.g + 8) * uni_delta;
     uni_c0 = cgp_exp(cov.h00 * k0 * k0); uni_c1 = cgp_exp(cov.h00 * k1 * k1);
+    const double k2 = (double)(L.g + 16) * uni_delta;
+    uni_c2 = cgp_exp(cov.h00 * k2 * k2);
     uni_2hd = 2.0 * cov.h00 * uni_delta;
   }
   int64_t w = blockIdx.x, w_nxt = (int64_t)blockIdx.x + gridDim.x, t_next = 0;
@@ -614,16 +616,20 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
 
     if (FUSED || PF) {
       // ---------------- U blocks of 8 grid points per pass (CGP64_GRID_U, 1 or 2)
-      constexpr int U = CGP64_GRID_U;
+      constexpr int UB = CGP64_GRID_U;                     // blocks per regular pass
+      // uniform shared grid, one CTA per object: passes of THREE blocks (and at most two of two) cover the grid exactly, instead
+      // of passes of two whose last one runs past the end of the grid (M = 100: 13 blocks = 3 + 3 + 3 + 2 + 2 instead of 7 x 2)
+      constexpr bool TAIL3 = UNI && PF && UB == 2 && WPC == 1;
+      constexpr int UMAX = TAIL3 ? 3 : UB;
       const int64_t g0 = a.goff ? a.goff[b] : 0;
       const int64_t m_pts = a.goff ? (a.goff[b + 1] - g0) : a.m_shared;
       const int64_t out0 = a.goff ? g0 : b * a.m_shared;
       const int64_t n_rb = (m_pts + 7) >> 3;
       const double amp_star = cov.amp_auto + cov.nugget2;
-      double pgx[U], pgy[U], pny0[U];
+      double pgx[UMAX], pgy[UMAX], pny0[UMAX];
       auto grid_fetch = [&](int64_t rb) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < UMAX; ++u) {
           const int64_t m = 8 * (rb + u) + L.g;
           const bool lv = m < m_pts;
           pgx[u] = 0.0; pgy[u] = 0.0;
@@ -634,9 +640,10 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           pny0[u] = (lv && a.new_y0) ? (a.new_y0_diff ? a.new_y0[m] + a.new_y0_diff[b] : a.new_y0[out0 + m]) : 0.0;
         }
       };
-      const int64_t rb0 = (int64_t)(part * WPC + warp) * U, rbs = (int64_t)split * WPC * U;   // the warps of a CTA alternate over the passes
+      const int64_t rb0 = (int64_t)(part * WPC + warp) * UB, rbs = (int64_t)split * WPC * UB;   // the warps of a CTA alternate over the passes
       grid_fetch(rb0);
-      for (int64_t rb = rb0; rb < n_rb; rb += rbs) {
+      auto pass = [&](auto Uc, const int64_t rb, const int64_t rb_next) {
+        constexpr int U = decltype(Uc)::value;
         int64_t mi[U]; bool live[U]; double gx[U], gy[U], ny0[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -644,7 +651,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           live[u] = mi[u] < m_pts;
           gx[u] = pgx[u]; gy[u] = pgy[u]; ny0[u] = pny0[u];
         }
-        grid_fetch(rb + rbs);                              // next pair's coordinates, behind this pair's math
+        grid_fetch(rb_next);                               // next pass's coordinates, behind this pass's math
         // cross-covariance fragments (no amplitude), generated straight into the accumulators of the forward
         // substitution: lane (g,t) holds H[grid row g][columns 8P+2t, 8P+2t+1] = the start value of W_P
         double acc0[U][NB], acc1[U][NB];
@@ -653,6 +660,7 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
           // the anchors serve 16 grid rows: with one block per pass they are computed for every even block and the odd
           // block that follows reuses them (rows g + 8); blocks that do not follow each other (split > 1) get their own
           const bool second = (U == 1) && (rbs == 1) && (rb & 1);
+          (void)second;
           if (!second) {
           __syncwarp();                                        // the previous pass has read its anchors
           const double gj0 = fma((double)(8 * rb), uni_delta, uni_g0);
@@ -681,10 +689,10 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
             if (b2) { p0 *= r02; p1 *= r12; }
             if (b4) { p0 *= r04; p1 *= r14; }
             const double t0 = A0.x * p0, t1 = A1.x * p1;
-            if constexpr (U == 2) {
-              const double e00 = t0 * uni_c0, e01 = (t0 * r08) * uni_c1;
-              const double e10 = t1 * uni_c0, e11 = (t1 * r18) * uni_c1;
-              acc0[0][P] = e00; acc0[1][P] = e01; acc1[0][P] = e10; acc1[1][P] = e11;
+            if constexpr (U >= 2) {
+              const double s0 = t0 * r08, s1 = t1 * r18;           // E R^(g+8): multiplied up in this order nothing overflows
+              acc0[0][P] = t0 * uni_c0; acc0[1][P] = s0 * uni_c1; acc1[0][P] = t1 * uni_c0; acc1[1][P] = s1 * uni_c1;
+              if constexpr (U == 3) { acc0[2][P] = (s0 * r08) * uni_c2; acc1[2][P] = (s1 * r18) * uni_c2; }
             } else {
               const double cs = second ? uni_c1 : uni_c0;
               acc0[0][P] = (second ? t0 * r08 : t0) * cs; acc1[0][P] = (second ? t1 * r18 : t1) * cs;
@@ -749,6 +757,18 @@ gp64_kernel(const SmallArgs a, unsigned long long* __restrict__ ticket) {
             if (a.var) a.var[out0 + mi[u]] = var;
           }
         }
+      };
+      if (TAIL3 && rbs == UB) {
+        // the whole grid belongs to this warp: cover its n_rb blocks exactly with passes of three (three interleaved
+        // substitutions hide each other's dependent DMMA chains better than two, and the anchors and the 36 tile loads
+        // of a pass serve 24 rows) and at most two passes of two
+        for (int64_t rb = rb0; rb < n_rb;) {
+          const int64_t left = n_rb - rb;
+          if (left == 1 || left == 2 || left == 4) { pass(std::integral_constant<int, UB>{}, rb, rb + UB); rb += UB; }
+          else { pass(std::integral_constant<int, UMAX>{}, rb, rb + UMAX); rb += UMAX; }
+        }
+      } else {
+        for (int64_t rb = rb0; rb < n_rb; rb += rbs) pass(std::integral_constant<int, UB>{}, rb, rb + rbs);
       }
     }
   }
