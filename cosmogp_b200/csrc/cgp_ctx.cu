@@ -54,7 +54,11 @@ bool load_nccl(std::string* why) {
     h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
     if (h) break;
   }
-  if (!h) { if (why) *why = std::string("libnccl.so.2 not found (") + (dlerror() ? dlerror() : "") + ")"; return false; }
+  if (!h) {
+    const char* err = dlerror();          // a second call would return NULL: the message is cleared by the first
+    if (why) *why = std::string("libnccl.so.2 not found (") + (err ? err : "") + ")";
+    return false;
+  }
   g_nccl.handle = h;
 #define CGP_SYM(field, name) g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name))
   CGP_SYM(CommInitAll, "ncclCommInitAll"); CGP_SYM(CommDestroy, "ncclCommDestroy");

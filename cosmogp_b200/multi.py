@@ -67,6 +67,7 @@ class ShardedBatch:
         L.cgp_ctx_batch_ranges(self._batch, starts.ctypes.data)
         self.ranges = [(int(starts[d]), int(starts[d + 1])) for d in range(self.n_devices)]
         self._tot = C.c_double(0.0)
+        self._last = None
 
     def close(self):
         L = _lib.lib()
@@ -99,6 +100,8 @@ class ShardedBatch:
         return float(self._tot.value), int(rc)
 
     def _ll_full(self):
+        if self._last is None:
+            raise RuntimeError("no likelihood has been evaluated on this batch yet (call log_likelihood_total first)")
         h, nugget, floor, flags = self._last
         ll = np.empty(max(self.n_obj, 1)); info = np.zeros(max(self.n_obj, 1), dtype=np.int32)
         _lib.check(_lib.lib().cgp_ctx_batch_ll(self._batch, _lib.hptr(h), nugget, floor, flags, C.byref(self._tot),
