@@ -19,6 +19,7 @@
 // m8n8k4 layouts (A[g][k], B[k][g], C[g][2t..2t+1]) this gives all three products the algorithm needs,
 //   X*Y^T (frag, frag)   X*Y (frag, fragT)   X^T*Y (fragT, fragT),
 // and lets a tile that was just accumulated feed the next DMMA straight from its registers.
+#include <type_traits>
 #include "cgp_internal.h"
 #include "cgp_math.cuh"
 
@@ -74,6 +75,15 @@ __device__ __forceinline__ double red_g(double v) {     // sum over the 8 row gr
   return v;
 }
 __device__ __forceinline__ double red_warp(double v) { return red_g(red_t(v)); }
+
+// f(integral_constant<int, I>) for I = BEGIN .. END-1, unrolled by the template machinery
+template <int BEGIN, int END, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (BEGIN < END) {
+    f(std::integral_constant<int, BEGIN>{});
+    static_for<BEGIN + 1, END>(f);
+  }
+}
 
 template <int WARPS> __device__ __forceinline__ void cta_sync() {
   if (WARPS == 1) __syncwarp(); else __syncthreads();
@@ -159,19 +169,20 @@ __device__ __forceinline__ void k_tile_minus(const Cov& cov, const double* px, c
   if (cj + 1 == gi) k1 = dg - s1;
 }
 
-template <int DIM, int TASK, int NB_MAX, int WARPS>
+template <int DIM, int TASK, int NB_MAX, int WARPS, bool FWD_BIG = false>
 __global__ void __launch_bounds__(WARPS * 32)
-small_gp_kernel(const SmallArgs a, const int nbm) {
+small_gp_kernel(const SmallArgs a, const int nbm, const int mode) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Lane L(lane);
   Cov cov = a.cov;
   constexpr int NT = WARPS * 32;
   constexpr int KMAX = (NB_MAX - 1 + WARPS - 1) / WARPS;   // L^-1 row: tiles per warp
-  // Prediction by block forward substitution (no L^-1, see below) up to 128 points.  Beyond, one object fills the shared
-  // memory of an SM (one warp per sub-partition) and the 28 dependent steps of the substitution are exposed: there the
-  // product with an explicit L^-1 (28 independent accumulator chains per grid block) stays faster (N = 224: 14 vs 21 ms).
-  constexpr bool FWD = (TASK == TASK_PREDICT) && NB_MAX <= 16;
+  // Prediction by block forward substitution (no L^-1, see below).  FWD_BIG selects it above 128 points as well (eight
+  // warps, one object per SM; N = 224: 6.4 ms against 8.6 ms through an explicit L^-1 -- once the 406-tile triangle is
+  // unrolled by template recursion; left to the loop unroller its accumulators went to local memory: 21 ms).  The
+  // L^-1 product of the grid phase further down remains for CGP_BIG_FWD=0 and CGP_BIG_WARPS=4.
+  constexpr bool FWD = (TASK == TASK_PREDICT) && (NB_MAX <= 16 || FWD_BIG);
 
   const int ld = 8 * nbm;
   double* tiles = smem;                                   // nbm(nbm+1)/2 tiles
@@ -183,7 +194,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
   double* vd = va + ld;                                   // diag(K^-1)
   double* v1 = vd + ld;                                   // L^-1 1
   double* vu = v1 + ld;                                   // K^-1 1
-  __shared__ double s_rsum;
+  __shared__ double s_rsum, s_quad;
   __shared__ int s_bad;
 
   const int split = (TASK == TASK_PREDICT) ? a.split : 1;
@@ -231,38 +242,103 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
     // ---------------- left-looking block Cholesky; slot(J,J) receives T_J = L_JJ^-1.
     // log det accumulates as mantissa * 2^exponent of the pivot product (one log per object).
     double lp_m = 1.0; int lp_e = 0;
+    // mode bit 0 (diagonal warp): warp 0 owns the diagonal tile alone -- its eight serial pivots are the critical path of
+    // a column -- while the other warps share the off-diagonal tiles, instead of taking an equal share of the column first.
+    // mode bit 1 (look-ahead): the rank-8(J-1) part of C[J][J] is accumulated one column early by the last warp and parked
+    // in slot(J,J); warp 0 solves L[J][J-1] itself right after T_{J-1}, subtracts its square and carries C[J][J] in
+    // registers into the next column: it only ARRIVES at the barrier that ends the solve phase, so that the chain
+    // pivots -> one panel tile -> one rank-8 update -> pivots is all that is left on the critical path.
+    const bool dwarp = WARPS > 1 && (mode & 1);
+    const bool la = dwarp && (mode & 2);
+    // sum_{P<cnt} X[row][P] X[row][P]^T: both operands are the same fragment; four chains (k-halves x parity of P)
+    auto self_syrk = [&](int row, int cnt, double& r0, double& r1) {
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+      const double* tj = tiles + slot(row, 0) * TILE + L.fr;
+      int P = 0;
+      for (; P + 1 < cnt; P += 2) {
+        const double2 f = *reinterpret_cast<const double2*>(tj + P * TILE);
+        const double2 g = *reinterpret_cast<const double2*>(tj + (P + 1) * TILE);
+        dmma(a0, a1, f.x, f.x); dmma(b0, b1, f.y, f.y);
+        dmma(c0, c1, g.x, g.x); dmma(d0, d1, g.y, g.y);
+      }
+      if (P < cnt) {
+        const double2 f = *reinterpret_cast<const double2*>(tj + P * TILE);
+        dmma(a0, a1, f.x, f.x); dmma(b0, b1, f.y, f.y);
+      }
+      r0 = (a0 + b0) + (c0 + d0); r1 = (a1 + b1) + (c1 + d1);
+    };
+    // mode bit 2 (z in the loop): z = L^-1 r rides along as one more row -- the last warp forms r_J - sum L[J][P] z_P
+    // beside the tiles of column J and multiplies by T_J in the solve phase -- instead of a serial substitution by
+    // warp 0 after the factorisation, which the other warps spend at the barrier of the next object.
+    // (prediction with several CTAs per SM: measured slower, 4.16 -> 4.55 ms at N = 128; with one object per SM it pays)
+    constexpr bool ZTASK = (TASK == TASK_LL && WARPS > 1) || (FWD && WARPS >= 8 && NB_MAX > 16);
+    const bool zin = ZTASK && (mode & 4);
+    double zquad = 0.0;
+    double ck0 = 0.0, ck1 = 0.0;                           // look-ahead: C[J][J], carried by warp 0 out of column J-1
     for (int J = 0; J < nb; ++J) {
+      auto finish_diag = [&](double k0, double k1) {
+        double t0, t1, piv; int badk;
+        diag_factor(k0, k1, L, t0, t1, piv, badk);
+        st_acc(tiles, slot(J, J), L, t0, t1);
+        if (TASK == TASK_LL || TASK == TASK_MATRICES) {
+          lp_m *= piv;
+          const int hi = __double2hiint(lp_m);
+          const int e = ((hi >> 20) & 0x7ff) - 1023;
+          lp_e += e;
+          lp_m = __hiloint2double(hi - (e << 20), __double2loint(lp_m));
+        }
+        if (badk && lane == 0 && s_bad == 0) s_bad = 8 * J + badk;
+      };
+      double dk0 = 0.0, dk1 = 0.0;                         // C[J][J] in warp 0, factorised once its other tiles are parked
+      if (dwarp && warp == 0) {
+        if (la && J > 0) { dk0 = ck0; dk1 = ck1; }
+        else {
+          double r0, r1;
+          self_syrk(J, J, r0, r1);
+          k_tile_minus<DIM>(cov, px, noise, ld, n, J, J, L, r0, r1, dk0, dk1, amat, a.lda);
+        }
+      }
       // tiles of block column J owned by this warp, two at a time; each tile accumulates its
       // rank-8J update on two independent DMMA chains (k-halves) -> 4 chains in flight
-      for (int I = J + warp; I < nb; I += 2 * WARPS) {
-        const int I2 = I + WARPS;
+      const int nw = dwarp ? WARPS - 1 : WARPS;
+      const int i_first = dwarp ? (warp == 0 ? nb : J + warp) : J + warp;
+      for (int I = i_first; I < nb; I += 2 * nw) {
+        const int I2 = I + nw;
         const bool two = I2 < nb;
         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
         const double* tj = tiles + slot(J, 0) * TILE + L.fr;
         const double* ti = tiles + slot(I, 0) * TILE + L.fr;
         const double* ti2 = tiles + slot(two ? I2 : I, 0) * TILE + L.fr;
+        if (two) {
 #pragma unroll 2
-        for (int P = 0; P < J; ++P) {
-          const double2 fb = *reinterpret_cast<const double2*>(tj + P * TILE);
-          const double2 fa = *reinterpret_cast<const double2*>(ti + P * TILE);
-          const double2 fc = *reinterpret_cast<const double2*>(ti2 + P * TILE);
-          dmma(a0, a1, fa.x, fb.x); dmma(b0, b1, fa.y, fb.y);
-          dmma(c0, c1, fc.x, fb.x); dmma(d0, d1, fc.y, fb.y);
+          for (int P = 0; P < J; ++P) {
+            const double2 fb = *reinterpret_cast<const double2*>(tj + P * TILE);
+            const double2 fa = *reinterpret_cast<const double2*>(ti + P * TILE);
+            const double2 fc = *reinterpret_cast<const double2*>(ti2 + P * TILE);
+            dmma(a0, a1, fa.x, fb.x); dmma(b0, b1, fa.y, fb.y);
+            dmma(c0, c1, fc.x, fb.x); dmma(d0, d1, fc.y, fb.y);
+          }
+        } else {                                          // a single tile: the four chains split P by parity instead
+          int P = 0;
+          for (; P + 1 < J; P += 2) {
+            const double2 fb = *reinterpret_cast<const double2*>(tj + P * TILE);
+            const double2 fa = *reinterpret_cast<const double2*>(ti + P * TILE);
+            const double2 gb = *reinterpret_cast<const double2*>(tj + (P + 1) * TILE);
+            const double2 ga = *reinterpret_cast<const double2*>(ti + (P + 1) * TILE);
+            dmma(a0, a1, fa.x, fb.x); dmma(b0, b1, fa.y, fb.y);
+            dmma(c0, c1, ga.x, gb.x); dmma(d0, d1, ga.y, gb.y);
+          }
+          if (P < J) {
+            const double2 fb = *reinterpret_cast<const double2*>(tj + P * TILE);
+            const double2 fa = *reinterpret_cast<const double2*>(ti + P * TILE);
+            dmma(a0, a1, fa.x, fb.x); dmma(b0, b1, fa.y, fb.y);
+          }
+          a0 += c0; a1 += c1; b0 += d0; b1 += d1;
         }
         double k0, k1;
         k_tile_minus<DIM>(cov, px, noise, ld, n, I, J, L, a0 + b0, a1 + b1, k0, k1, amat, a.lda);
-        if (I == J) {                                     // warp 0
-          double t0, t1, piv; int badk;
-          diag_factor(k0, k1, L, t0, t1, piv, badk);
-          st_acc(tiles, slot(J, J), L, t0, t1);
-          if (TASK == TASK_LL || TASK == TASK_MATRICES) {
-            lp_m *= piv;
-            const int hi = __double2hiint(lp_m);
-            const int e = ((hi >> 20) & 0x7ff) - 1023;
-            lp_e += e;
-            lp_m = __hiloint2double(hi - (e << 20), __double2loint(lp_m));
-          }
-          if (badk && lane == 0 && s_bad == 0) s_bad = 8 * J + badk;
+        if (I == J) {                                     // warp 0 (only without a dedicated diagonal warp)
+          dk0 = k0; dk1 = k1;
         } else {
           st_acc(tiles, slot(I, J), L, k0, k1);           // park C[I][J] in its own slot
         }
@@ -271,26 +347,81 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
           st_acc(tiles, slot(I2, J), L, k0, k1);
         }
       }
+      if (la && warp == WARPS - 1 && J + 1 < nb) {        // next diagonal tile, all but its last rank-8 term
+        double r0, r1, k0, k1;
+        self_syrk(J + 1, J, r0, r1);
+        k_tile_minus<DIM>(cov, px, noise, ld, n, J + 1, J + 1, L, r0, r1, k0, k1, amat, a.lda);
+        st_acc(tiles, slot(J + 1, J + 1), L, k0, k1);
+      }
+      double zw = 0.0;
+      if (ZTASK && zin && warp == WARPS - 1) {
+        double p = 0.0, p2 = 0.0;
+        const double* tj = tiles + slot(J, 0) * TILE + L.fr;
+        for (int P = 0; P < J; ++P) {
+          const double2 f = *reinterpret_cast<const double2*>(tj + P * TILE);
+          p = fma(f.x, vr[8 * P + 2 * L.t], p); p2 = fma(f.y, vr[8 * P + 2 * L.t + 1], p2);
+        }
+        zw = FWD ? vr[8 * J + L.g] + red_t(p + p2) : vr[8 * J + L.g] - red_t(p + p2);      // FWD: the tiles hold -L
+      }
+      if (warp == 0) finish_diag(dk0, dk1);
       cta_sync<WARPS>();
       const double2 ft = ld_frag(tiles, slot(J, J), L);
-      for (int I = J + 1 + warp; I < nb; I += 2 * WARPS) {    // L[I][J] = C[I][J] T_J^T
-        const int I2 = I + WARPS;
-        const bool two = I2 < nb;
-        const double2 fc = ld_frag(tiles, slot(I, J), L);
-        const double2 fe = ld_frag(tiles, slot(two ? I2 : I, J), L);
-        double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
-        dmma(d0, d1, fc.x, ft.x); dmma(e0, e1, fc.y, ft.y);
-        dmma(f0, f1, fe.x, ft.x); dmma(g0, g1, fe.y, ft.y);
-        __syncwarp();
-        // prediction keeps -L below the diagonal: the forward substitution of the grid phase then accumulates
-        // h + sum V_P (-L[J][P])^T directly (the rank updates of later columns do not notice the sign)
-        constexpr double sgn = FWD ? -1.0 : 1.0;
-        st_acc(tiles, slot(I, J), L, sgn * (d0 + e0), sgn * (d1 + e1));
-        if (two) st_acc(tiles, slot(I2, J), L, sgn * (f0 + g0), sgn * (f1 + g1));
+      if (ZTASK && zin && warp == WARPS - 1) {
+        double q = ft.x * __shfl_sync(FULL, zw, L.t * 8) + ft.y * __shfl_sync(FULL, zw, L.t * 8 + 4);
+        q = red_t(q);
+        if (L.t == 0) { vr[8 * J + L.g] = q; zquad = fma(q, q, zquad); }
+      }
+      // prediction keeps -L below the diagonal: the forward substitution of the grid phase then accumulates
+      // h + sum V_P (-L[J][P])^T directly (the rank updates of later columns do not notice the sign)
+      constexpr double sgn = FWD ? -1.0 : 1.0;
+      if (la && warp == 0) {
+        if (J + 1 < nb) {
+          const double2 fc = ld_frag(tiles, slot(J + 1, J), L);
+          double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, m0 = 0.0, m1 = 0.0, q0 = 0.0, q1 = 0.0;
+          dmma(d0, d1, fc.x, ft.x); dmma(e0, e1, fc.y, ft.y);
+          const double2 dp = ld_frag(tiles, slot(J + 1, J + 1), L);
+          const double l0 = d0 + e0, l1 = d1 + e1;          // the accumulator pair is the operand fragment of the tile
+          __syncwarp();
+          st_acc(tiles, slot(J + 1, J), L, sgn * l0, sgn * l1);
+          dmma(m0, m1, l0, l0); dmma(q0, q1, l1, l1);
+          ck0 = dp.x - (m0 + q0); ck1 = dp.y - (m1 + q1);
+        }
+        asm volatile("bar.arrive 1, %0;" :: "r"(NT) : "memory");
+      } else {
+        const int s_first = J + 1 + warp;                   // with look-ahead warp 0 is not here: rows J+2.. over warps 1..
+        const int s_nw = la ? WARPS - 1 : WARPS;
+        for (int I = s_first; I < nb; I += 2 * s_nw) {      // L[I][J] = C[I][J] T_J^T
+          const int I2 = I + s_nw;
+          const bool two = I2 < nb;
+          const double2 fc = ld_frag(tiles, slot(I, J), L);
+          const double2 fe = ld_frag(tiles, slot(two ? I2 : I, J), L);
+          double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
+          dmma(d0, d1, fc.x, ft.x); dmma(e0, e1, fc.y, ft.y);
+          if (two) { dmma(f0, f1, fe.x, ft.x); dmma(g0, g1, fe.y, ft.y); }
+          __syncwarp();
+          st_acc(tiles, slot(I, J), L, sgn * (d0 + e0), sgn * (d1 + e1));
+          if (two) st_acc(tiles, slot(I2, J), L, sgn * (f0 + g0), sgn * (f1 + g1));
+        }
+        if (la) asm volatile("bar.sync 1, %0;" :: "r"(NT) : "memory");
+        else cta_sync<WARPS>();
+      }
+    }
+    if (la) cta_sync<WARPS>();                              // warp 0 ran ahead of the last solve phases
+
+    if (TASK == TASK_LL && ZTASK && zin) {
+      if (warp == WARPS - 1) {
+        zquad = red_warp(zquad);
+        if (lane == 0) s_quad = zquad;
       }
       cta_sync<WARPS>();
+      if (tid == 0) {                                     // log det lives in warp 0
+        const int bad = s_bad;
+        a.info[io] = bad;
+        const double logdet = log(lp_m) + (double)lp_e * 0.693147180559945309417232;
+        a.ll[io] = bad ? nan("") : -0.5 * (s_quad + logdet + n * LOG_2PI);
+      }
+      continue;
     }
-
     if (TASK == TASK_LL) {
       // ---------------- z = L^-1 r by block forward substitution (warp 0), quad = |z|^2
       if (warp == 0) {
@@ -325,7 +456,7 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
       // then per block of 8 grid points the same substitution for the cross-covariance rows ON THE TENSOR CORES:
       // V_P = W_P T_P^T (operands: the accumulator registers and the T_P tile), W_J += V_P (-L[J][P])^T for J > P;
       // mean = v . z + y0*, var = amp* - |v|^2.  h is kept WITHOUT its amplitude (applied once per grid point).
-      if (warp == 0) {
+      if (warp == 0 && !(ZTASK && zin)) {
         for (int J = 0; J < nb; ++J) {
           double p = 0.0, p2 = 0.0;
           const double* tj = tiles + slot(J, 0) * TILE + L.fr;
@@ -368,8 +499,10 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
           }
         }
         double pm = 0.0, pm2 = 0.0, vv = 0.0, vv2 = 0.0;
-#pragma unroll
-        for (int P = 0; P < NB_MAX; ++P) {
+        // unrolled by template recursion: the accumulators must stay in registers, and at NB_MAX = 28 the loop unroller
+        // gives up on the 406-tile triangle (the arrays then live in local memory: 544 bytes of stack, 21 ms instead of 14)
+        static_for<0, NB_MAX>([&](auto Pc) {
+          constexpr int P = decltype(Pc)::value;
           if (P < nb) {
             const double2 ft = ld_frag(tiles, slot(P, P), L);
             double r0 = 0.0, r1 = 0.0, e0 = 0.0, e1 = 0.0;
@@ -380,15 +513,15 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
             vv = fma(v0, v0, vv); vv2 = fma(v1, v1, vv2);
             if (a.vout && live)                           // bulk covariance writer (cgp_covariance_batched_dev)
               *reinterpret_cast<double2*>(a.vout + (out0 + mi) * ld + 8 * P + 2 * L.t) = make_double2(v0, v1);
-#pragma unroll
-            for (int J = P + 1; J < NB_MAX; ++J) {        // compile-time triangle: no wasted DMMA
+            static_for<P + 1, NB_MAX>([&](auto Jc) {      // compile-time triangle: no wasted DMMA
+              constexpr int J = decltype(Jc)::value;
               if (J < nb) {
                 const double2 fb = ld_frag(tiles, slot(J, P), L);
                 dmma(acc0[J], acc1[J], v0, fb.x); dmma(acc0[J], acc1[J], v1, fb.y);
               }
-            }
+            });
           }
-        }
+        });
         pm = red_t(pm + pm2); vv = red_t(vv + vv2);
         if (live && L.t == 0) {
           const double m0 = !a.new_y0 ? 0.0 : (a.new_y0_diff ? a.new_y0[mi] + a.new_y0_diff[b] : a.new_y0[out0 + mi]);
@@ -619,9 +752,9 @@ small_gp_kernel(const SmallArgs a, const int nbm) {
 }
 
 // ---------------------------------------------------------------------------------------
-template <int DIM, int TASK, int NB_MAX, int WARPS>
+template <int DIM, int TASK, int NB_MAX, int WARPS, bool FWD_BIG = false>
 int launch_one(int nbm, const SmallArgs& a, cudaStream_t stream) {
-  auto kern = small_gp_kernel<DIM, TASK, NB_MAX, WARPS>;
+  auto kern = small_gp_kernel<DIM, TASK, NB_MAX, WARPS, FWD_BIG>;
   const size_t smem = small_smem_bytes((Task)TASK, DIM, nbm);
   static int sm_count = 0;
   if (!sm_count) {
@@ -638,7 +771,14 @@ int launch_one(int nbm, const SmallArgs& a, cudaStream_t stream) {
   int64_t grid = (int64_t)sm_count * per_sm;
   if (grid > n_work) grid = n_work;
   if (grid < 1) return 0;
-  kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(a, nbm);
+  // the Cholesky schedule of the kernel (see its column loop): CGP_DIAG_WARP=0|1, CGP_LOOKAHEAD=0|1, CGP_Z_IN_LOOP=0|1
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("CGP_DIAG_WARP"); const char* f = getenv("CGP_LOOKAHEAD"); const char* g = getenv("CGP_Z_IN_LOOP");
+    mode = ((e ? atoi(e) : 1) ? 1 : 0) | ((f ? atoi(f) : 0) ? 2 : 0) | ((g ? atoi(g) : 1) ? 4 : 0);
+  }
+  const int dw = mode;
+  kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(a, nbm, dw);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -670,6 +810,9 @@ int launch_cfg(int nbm, const SmallArgs& a, cudaStream_t stream) {
   static int big = -1;
   if (big < 0) { const char* e = getenv("CGP_BIG_WARPS"); big = (e && atoi(e) == 4) ? 4 : 8; }
   if (big == 4 || TASK == TASK_MATRICES) return launch_one<DIM, TASK, 28, 4>(nbm, a, stream);
+  static int bigfwd = -1;
+  if (bigfwd < 0) { const char* e = getenv("CGP_BIG_FWD"); bigfwd = e ? atoi(e) : 1; }
+  if (TASK == TASK_PREDICT && bigfwd) return launch_one<DIM, TASK, 28, 8, true>(nbm, a, stream);
   return launch_one<DIM, TASK, 28, 8>(nbm, a, stream);
 }
 
