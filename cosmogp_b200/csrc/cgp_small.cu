@@ -169,6 +169,36 @@ __device__ __forceinline__ void k_tile_minus(const Cov& cov, const double* px, c
   if (cj + 1 == gi) k1 = dg - s1;
 }
 
+// The tiles (I,J) and (I2,J), I2 > I >= J, of one block column at once: the four exp chains of a lane sit in one
+// straight line and interleave (two calls of k_tile_minus are separated by its branch on `amat`).  (I2,J) is never diagonal.
+template <int DIM>
+__device__ __forceinline__ void k_tile2_minus(const Cov& cov, const double* px, const double* noise, int ld, int n,
+                                              int I, int I2, int J, const Lane& L, double s0, double s1, double u0, double u1,
+                                              double& k0, double& k1, double& m0, double& m1,
+                                              const double* amat = nullptr, int64_t lda = 0) {
+  if (amat) {
+    k_tile_minus<DIM>(cov, px, noise, ld, n, I, J, L, s0, s1, k0, k1, amat, lda);
+    k_tile_minus<DIM>(cov, px, noise, ld, n, I2, J, L, u0, u1, m0, m1, amat, lda);
+    return;
+  }
+  const int gi = 8 * I + L.g, gi2 = 8 * I2 + L.g, cj = 8 * J + 2 * L.t;
+  double e0 = cov_e<DIM>(cov, px, ld, gi, cj);
+  double e1 = cov_e<DIM>(cov, px, ld, gi, cj + 1);
+  double f0 = cov_e<DIM>(cov, px, ld, gi2, cj);
+  double f1 = cov_e<DIM>(cov, px, ld, gi2, cj + 1);
+  e0 = (gi < n && cj < gi) ? e0 : 0.0;
+  e1 = (gi < n && cj + 1 < gi) ? e1 : 0.0;
+  f0 = (gi2 < n) ? f0 : 0.0;                              // cj + 1 < 8 (J + 1) <= 8 I2 <= gi2
+  f1 = (gi2 < n) ? f1 : 0.0;
+  k0 = fma(cov.amp_auto, e0, -s0);
+  k1 = fma(cov.amp_auto, e1, -s1);
+  m0 = fma(cov.amp_auto, f0, -u0);
+  m1 = fma(cov.amp_auto, f1, -u1);
+  const double dg = (gi < n) ? cov.amp_auto + noise[gi] : 1.0;
+  if (cj == gi) k0 = dg - s0;
+  if (cj + 1 == gi) k1 = dg - s1;
+}
+
 template <int DIM, int TASK, int NB_MAX, int WARPS, bool FWD_BIG = false>
 __global__ void __launch_bounds__(WARPS * 32)
 small_gp_kernel(const SmallArgs a, const int nbm, const int mode) {
@@ -335,17 +365,16 @@ small_gp_kernel(const SmallArgs a, const int nbm, const int mode) {
           }
           a0 += c0; a1 += c1; b0 += d0; b1 += d1;
         }
-        double k0, k1;
-        k_tile_minus<DIM>(cov, px, noise, ld, n, I, J, L, a0 + b0, a1 + b1, k0, k1, amat, a.lda);
+        // both covariance tiles of a pair before either store: their four exp chains interleave in one straight line
+        double k0, k1, m0 = 0.0, m1 = 0.0;
+        if (two) k_tile2_minus<DIM>(cov, px, noise, ld, n, I, I2, J, L, a0 + b0, a1 + b1, c0 + d0, c1 + d1, k0, k1, m0, m1, amat, a.lda);
+        else k_tile_minus<DIM>(cov, px, noise, ld, n, I, J, L, a0 + b0, a1 + b1, k0, k1, amat, a.lda);
         if (I == J) {                                     // warp 0 (only without a dedicated diagonal warp)
           dk0 = k0; dk1 = k1;
         } else {
           st_acc(tiles, slot(I, J), L, k0, k1);           // park C[I][J] in its own slot
         }
-        if (two) {
-          k_tile_minus<DIM>(cov, px, noise, ld, n, I2, J, L, c0 + d0, c1 + d1, k0, k1, amat, a.lda);
-          st_acc(tiles, slot(I2, J), L, k0, k1);
-        }
+        if (two) st_acc(tiles, slot(I2, J), L, m0, m1);
       }
       if (la && warp == WARPS - 1 && J + 1 < nb) {        // next diagonal tile, all but its last rank-8 term
         double r0, r1, k0, k1;
