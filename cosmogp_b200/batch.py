@@ -27,10 +27,14 @@ def pack_csr(seq, dim=1):
         b, n = seq.shape[0], seq.shape[1]
         flat = np.ascontiguousarray(seq, dtype=np.float64).reshape(b * n, *([2] if dim == 2 else []))
         return flat, np.arange(b + 1, dtype=np.int64) * n
-    arrs = _as_list_of_arrays(seq, dim)
+    want = 2 if dim == 2 else 1
+    if all(type(a) is np.ndarray and a.ndim == want and (dim == 1 or a.shape[1] == 2) for a in seq):
+        arrs = seq          # already per-object arrays of the right shape: no per-object conversion (0.6 s at 10^5 objects)
+    else:
+        arrs = _as_list_of_arrays(seq, dim)
     off = np.zeros(len(arrs) + 1, dtype=np.int64)
     if arrs:
-        off[1:] = np.cumsum([len(a) for a in arrs])
+        off[1:] = np.cumsum(np.fromiter(map(len, arrs), dtype=np.int64, count=len(arrs)))
         flat = np.ascontiguousarray(np.concatenate(arrs), dtype=np.float64)
     else:
         flat = np.zeros((0, 2) if dim == 2 else (0,), dtype=np.float64)

@@ -90,3 +90,39 @@ def test_reference_arm_times_the_unmodified_reference():
     if os.path.isdir(ref_root) and os.path.isdir(inst):
         for name in ("Gaussian_process.py", "kernel.py", "inv_matrix.py", "mean.py", "pull.py", "__init__.py"):
             assert open(os.path.join(ref_root, name), "rb").read() == open(os.path.join(inst, name), "rb").read(), name
+
+
+def test_pack_csr_fast_path_equals_per_object_conversion():
+    """pack_csr (what the facade does with the reference's lists of per-object arrays, Gaussian_process.py:156-169)
+    skips the per-object conversion when every element already is an ndarray of the right rank; both routes must give
+    the same flat float64 array and int64 offsets for ragged, empty, list-valued, float32, integer and xy-flat inputs."""
+    from cosmogp_b200.batch import pack_csr, _as_list_of_arrays
+
+    def slow(seq, dim):
+        arrs = _as_list_of_arrays(seq, dim)
+        off = np.zeros(len(arrs) + 1, dtype=np.int64)
+        if not arrs:
+            return np.zeros((0, 2) if dim == 2 else (0,)), off
+        off[1:] = np.cumsum([len(a) for a in arrs])
+        return np.ascontiguousarray(np.concatenate(arrs), dtype=np.float64), off
+
+    rng = np.random.default_rng(0)
+    cases = [
+        ([rng.standard_normal(n) for n in rng.integers(0, 70, 300)], 1),
+        ([rng.standard_normal((n, 2)) for n in rng.integers(0, 70, 300)], 2),
+        ([list(rng.standard_normal(n)) for n in rng.integers(1, 9, 40)], 1),
+        ([rng.standard_normal(n).astype(np.float32) for n in rng.integers(1, 9, 40)], 1),
+        ([rng.standard_normal((2 * n, 2))[::2] for n in rng.integers(1, 9, 40)], 2),        # non-contiguous views
+        ([rng.standard_normal(2 * n) for n in rng.integers(1, 9, 40)], 2),                  # flat xy pairs
+        ([], 1), ([], 2),
+        (tuple(rng.standard_normal(n) for n in (3, 4)), 1),
+        ([rng.integers(0, 5, 4) for _ in range(3)], 1),
+    ]
+    for seq, dim in cases:
+        flat, off = pack_csr(seq, dim)
+        rf, ro = slow(seq, dim)
+        assert flat.dtype == np.float64 and flat.flags.c_contiguous and off.dtype == np.int64
+        assert flat.shape == rf.shape and np.array_equal(flat, rf) and np.array_equal(off, ro)
+    # equal-length objects handed over as one ndarray
+    x = rng.standard_normal((5, 7)); f, o = pack_csr(x, 1)
+    assert np.array_equal(f, x.ravel()) and np.array_equal(o, np.arange(6) * 7)
