@@ -27,6 +27,8 @@ def pack_csr(seq, dim=1):
         b, n = seq.shape[0], seq.shape[1]
         flat = np.ascontiguousarray(seq, dtype=np.float64).reshape(b * n, *([2] if dim == 2 else []))
         return flat, np.arange(b + 1, dtype=np.int64) * n
+    if not hasattr(seq, '__len__'):
+        seq = list(seq)                                  # an iterator of per-object arrays
     want = 2 if dim == 2 else 1
     if all(type(a) is np.ndarray and a.ndim == want and (dim == 1 or a.shape[1] == 2) for a in seq):
         arrs = seq          # already per-object arrays of the right shape: no per-object conversion (0.6 s at 10^5 objects)

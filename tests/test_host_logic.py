@@ -123,6 +123,13 @@ def test_pack_csr_fast_path_equals_per_object_conversion():
         rf, ro = slow(seq, dim)
         assert flat.dtype == np.float64 and flat.flags.c_contiguous and off.dtype == np.int64
         assert flat.shape == rf.shape and np.array_equal(flat, rf) and np.array_equal(off, ro)
+    # an iterator and a list-like view are accepted like a list
+    from cosmogp_b200.batch import RaggedView
+    arrs = [rng.standard_normal(n) for n in (3, 0, 5)]
+    ref = pack_csr(arrs, 1)
+    for alt in ((a for a in arrs), RaggedView(ref[0], ref[1])):
+        f, o = pack_csr(alt, 1)
+        assert np.array_equal(f, ref[0]) and np.array_equal(o, ref[1])
     # equal-length objects handed over as one ndarray
     x = rng.standard_normal((5, 7)); f, o = pack_csr(x, 1)
     assert np.array_equal(f, x.ravel()) and np.array_equal(o, np.arange(6) * 7)
